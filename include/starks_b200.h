@@ -1,0 +1,98 @@
+/*
+ * starks_b200.h -- C ABI of libstarks_b200.so, the B200-native drop-in for the STARK
+ * prover's data-parallel hot path of computablelabs/starks.
+ *
+ * The reference is pure Python and has no FFI; the boundary it offers is the module
+ * surface of starks/fft.py, starks/merkle_tree.py and starks/fri.py as consumed by
+ * starks/stark.py:4-17,31-35,225,254-276.  Each entry point below names the reference
+ * function (file:line, relative to the upstream repository root) it replaces; the Python
+ * shim in starks_b200/ (ctypes) rebinds those functions onto these symbols, see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - A field element is 8 little-endian uint32 limbs holding the canonical residue
+ *     (IntegerModP.n, starks/modp.py:36).  The 32-byte big-endian form
+ *     (IntegerModP.to_bytes, starks/modp.py:94-95) exists only inside hashed bytes.
+ *   - Columns are contiguous arrays of elements; `*_stride` arguments are in elements.
+ *   - Pointers named d_* are device pointers (cudaMalloc / torch.Tensor.data_ptr());
+ *     pointers named h_* are host pointers (pinned memory makes the copies asynchronous).
+ *   - Every call returns 0 on success or an STK_E* code; stk_last_error() gives the text.
+ *   - Calls are asynchronous on the context's stream unless they return data to the host.
+ *   - There is no CPU fallback: without a CUDA device stk_init fails.
+ */
+#ifndef STARKS_B200_H
+#define STARKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stk_ctx stk_ctx;
+
+enum {
+  STK_OK = 0,
+  STK_EINVAL = 1,      /* bad argument (maps to ValueError / TypeError)          */
+  STK_ECUDA = 2,       /* CUDA runtime failure                                   */
+  STK_EUNSUPPORTED = 3,/* size / modulus outside what the kernels implement      */
+  STK_EINDEX = 4       /* input longer than the order of the root: the reference
+                          raises IndexError there (starks/fft.py:303-314)        */
+};
+
+/* ---- context ------------------------------------------------------------------ */
+int stk_version(void);
+int stk_init(int device, stk_ctx** ctx);
+void stk_destroy(stk_ctx* ctx);
+const char* stk_last_error(stk_ctx* ctx);
+/* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = the
+ * context's own stream. */
+int stk_set_stream(stk_ctx* ctx, void* cuda_stream);
+int stk_sync(stk_ctx* ctx);
+/* Modulus of IntegersModP(p) (starks/modp.py:25-106).  p = 2^256 - 351*2^32 + 1 selects
+ * the fast path; any other odd p < 2^256 runs 8-limb Montgomery. */
+int stk_field_set(stk_ctx* ctx, const uint32_t p[8]);
+
+/* ---- memory helpers (so a host language needs no CUDA binding of its own) -------- */
+int stk_dev_alloc(stk_ctx* ctx, uint64_t bytes, void** d_ptr);
+int stk_dev_free(stk_ctx* ctx, void* d_ptr);
+int stk_host_alloc(stk_ctx* ctx, uint64_t bytes, void** h_ptr); /* pinned */
+int stk_host_free(stk_ctx* ctx, void* h_ptr);
+int stk_memcpy_h2d(stk_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes);
+int stk_memcpy_d2h(stk_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes); /* synchronous */
+int stk_memcpy_d2d(stk_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes);
+int stk_memset(stk_ctx* ctx, void* d_dst, int value, uint64_t bytes);
+
+/* ---- NTT ------------------------------------------------------------------------ */
+/* fft_1d (starks/fft.py:316-331) for `batch` columns.  Column c reads n_in elements at
+ * d_in + c*in_stride (zero padded up to n, :323-324; n_in > n -> STK_EINDEX) and writes n
+ * elements at d_out + c*out_stride.  out[k] = sum_j in[j] * root^(jk); inverse uses
+ * root^-1 and scales by n^-1 (:327-328).  n must be the multiplicative order of root:
+ * powers of two >= 8 run the shared-memory radix-8 passes, anything else (n <= 4096, e.g.
+ * the reference test's n = 6 over p = 31) the direct DFT kernel (_simple_ft, :287-300). */
+int stk_ntt(stk_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint64_t in_stride, uint32_t* d_out,
+            uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse);
+/* Same, host buffers; columns are streamed through the device in chunks with the copies
+ * overlapping the transforms. */
+int stk_ntt_host(stk_ctx* ctx, const uint32_t* h_in, uint64_t n_in, uint64_t in_stride, uint32_t* h_out,
+                 uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse);
+/* mul_polys (starks/fft.py:334-345): NTT(a) .* NTT(b) through the inverse-root transform
+ * WITHOUT the 1/n scaling, exactly as the reference. */
+int stk_mul_polys(stk_ctx* ctx, const uint32_t* d_a, uint64_t na, const uint32_t* d_b, uint64_t nb,
+                  uint32_t* d_out, uint64_t n, const uint32_t root[8]);
+/* Pointwise helpers on device columns: out[i] = a[i] (op) b[i]; op 0 add, 1 sub, 2 mul. */
+int stk_vec_op(stk_ctx* ctx, int op, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, uint64_t n);
+/* get_power_cycle (starks/utils.py:30-38): out[i] = r^i, i < n (n = order of r). */
+int stk_power_cycle(stk_ctx* ctx, const uint32_t r[8], uint64_t n, uint32_t* d_out);
+
+/* ---- K0: integer-pipe microbenchmarks (roofline denominators) ---------------------- */
+/* which: 0 IMAD, 1 IMAD.WIDE, 2 IADD3, 3 IMAD.HI, 4 IADD3+LOP3+SHF (BLAKE2s mix),
+ * 5 field multiply, 6 NTT butterfly, 7 IMAD+IADD3, 8 IMAD.WIDE+IADD3, 9 carry-chain adds,
+ * 10 IMAD.WIDE.X carry rows.  Returns elapsed milliseconds and the number of
+ * operations (of the kind named) executed. */
+int stk_microbench(stk_ctx* ctx, int which, uint64_t iters, float* ms, double* ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARKS_B200_H */

@@ -1,0 +1,69 @@
+// ctx.h -- library context shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/starks_b200.h"
+#include "field.cuh"
+#include "hostmath.h"
+
+struct stk_table {
+  stk::fe root;     // canonical root the table was built for
+  uint64_t n;       // number of entries (w^0 .. w^(n-1)), twiddle form
+  int mont;         // built for the Montgomery field currently set?
+  stk::fe* d;
+};
+
+struct stk_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev[8] = {};
+  int sm_count = 148;
+  bool is_stark = true;
+  stk::fe p;
+  stk::MontField mont;
+  std::vector<stk_table> tables;
+  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t scratch_bytes[4] = {0, 0, 0, 0};
+  std::string err;
+};
+
+static inline int stk_fail(stk_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define STK_CUDA(c, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return stk_fail((c), STK_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                      __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define STK_TRY(expr)            \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != STK_OK) return rc_; \
+  } while (0)
+
+// internal helpers (ntt_api.cu)
+int stk_scratch(stk_ctx* c, int slot, uint64_t bytes, void** out);
+int stk_get_table(stk_ctx* c, const stk::fe& root, uint64_t n, const stk::fe** d_table);
+stk::fe stk_load_fe(const uint32_t* w);
+int stk_ntt_dev(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, stk::fe* d_out,
+                uint64_t out_stride, uint64_t n, uint64_t batch, const stk::fe& root, int inverse, int scale);
+// field-generic host helpers
+stk::fe stk_h_mul(stk_ctx* c, const stk::fe& a, const stk::fe& b);
+stk::fe stk_h_pow(stk_ctx* c, const stk::fe& a, uint64_t e);
+stk::fe stk_h_inv(stk_ctx* c, const stk::fe& a);
+stk::fe stk_h_to_tw(stk_ctx* c, const stk::fe& a);

@@ -1,0 +1,151 @@
+// ntt.cuh -- batched radix-2 NTT over Z/p as shared-memory-staged radix-8 passes.
+//
+// Replaces the reference's recursive decimation-in-time `_fft` / `fft_1d`
+// (starks/fft.py:303-331): natural-order input, natural-order output,
+// out[k] = sum_j in[j] * w^(jk).  All arithmetic is exact mod p, so any correct
+// factorisation is bit-identical to the reference.
+//
+// Factorisation used here: plain decimation-in-frequency over the global index J
+// (n = log2 N bits), cut into 1-3 passes.  A pass owns `k` consecutive index bits
+// [lo, lo+k); a CTA stages a tile of C * 2^k elements in shared memory (eight limb planes,
+// XOR-swizzled so every radix-8 round is bank-conflict free), runs the k butterfly levels
+// as in-register radix-8 (2^R) rounds -- the first round reads global memory directly, the
+// last one writes it directly -- and the final pass stores to the bit-reversed index, which
+// makes the output natural-order without a separate permutation pass.  The C "batch"
+// positions of a tile are chosen so that global accesses come in C*32-byte runs: the
+// lowest index bits in non-final passes, the highest ones (lowest after bit reversal)
+// in the final pass, or C whole columns when one pass covers the transform.
+//
+// Butterfly at level with half-size H:  (a, b) -> (a + b, (a - b) * w^((J mod H) * N/(2H))).
+// Twiddles come from one table W[e] = w^e (e < N) kept in HBM in "twiddle form".
+#pragma once
+#include "field.cuh"
+
+namespace stk {
+
+struct NttPass {
+  int n;         // log2 N
+  int lo;        // lowest index bit of this pass
+  int k;         // butterfly levels in this pass
+  int logC;      // log2 tile batch width
+  int logT;      // k + logC
+  int c_is_col;  // batch positions are whole columns (single-pass transforms)
+  int cb;        // index bit position of the batch bits (when !c_is_col)
+  int nl, sl, sh;  // deposit of blockIdx.x into the remaining index bits
+  int nrounds;
+  int r[8];      // log2 radix of each round
+  int final_pass;  // bit-reversed store
+  int do_scale;    // multiply by `scale` on the final store (inverse transform)
+  uint32_t n_in;   // valid input elements per column; above that the input is zero
+  uint32_t batch;  // number of columns
+  unsigned long long in_col_stride, out_col_stride;  // elements
+  const fe* in;
+  fe* out;
+  const fe* W;
+  fe scale;  // twiddle form
+};
+
+__device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >> 3) & 31u); }
+
+template <class F, int R>
+__device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
+                                          uint32_t Jcta, uint32_t col0, int a, bool first, bool last) {
+  constexpr int M = 1 << R;
+  const int logS = a + A.logC;
+  const uint32_t S = 1u << logS;
+  const uint32_t Cm = (1u << A.logC) - 1u;
+  const uint32_t ngroups = T >> R;
+  const int gshift = A.lo + a;  // global index stride of m is 2^gshift
+  for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
+    const uint32_t pos0 = ((g >> logS) << (logS + R)) | (g & (S - 1u));
+    const uint32_t j0 = pos0 >> A.logC, c0 = pos0 & Cm;
+    const uint32_t J0 = Jcta | (j0 << A.lo) | (A.c_is_col ? 0u : (c0 << A.cb));
+    const uint32_t col = A.c_is_col ? (col0 + c0) : col0;
+    const bool col_ok = col < A.batch;
+    fe x[M];
+    if (first) {
+      const fe* src = A.in + (unsigned long long)col * A.in_col_stride;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        uint32_t J = J0 + ((uint32_t)m << gshift);
+        x[m] = (col_ok && J < A.n_in) ? fe_load(src + J) : fe_zero();
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        uint32_t ph = sm_phys(pos0 + (uint32_t)m * S);
+#pragma unroll
+        for (int l = 0; l < 8; ++l) x[m].v[l] = sm[l * T + ph];
+      }
+    }
+    // exponent of the last (smallest-half) level of this round
+    const uint32_t Jl = J0 & ((1u << gshift) - 1u);
+    const uint32_t er = Jl << (A.n - 1 - gshift);
+#pragma unroll
+    for (int lv = 0; lv < R; ++lv) {
+      const int lh = R - 1 - lv;  // log2 of half size in m units
+      const int hm = 1 << lh;
+#pragma unroll
+      for (int mm = 0; mm < hm; ++mm) {
+        const uint32_t e = (er >> lh) + ((uint32_t)mm << (A.n - 1 - lh));
+        const fe tw = fe_load_ro(A.W + e);
+#pragma unroll
+        for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
+          const int i0 = blk * 2 * hm + mm, i1 = i0 + hm;
+          fe s = f.add(x[i0], x[i1]);
+          fe d = f.sub(x[i0], x[i1]);
+          x[i0] = s;
+          x[i1] = f.mul_tw(d, tw);
+        }
+      }
+    }
+    if (last) {
+      if (col_ok) {
+        fe* dst = A.out + (unsigned long long)col * A.out_col_stride;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          uint32_t J = J0 + ((uint32_t)m << gshift);
+          uint32_t K = A.final_pass ? (__brev(J) >> (32 - A.n)) : J;
+          fe v = x[m];
+          if (A.do_scale) v = f.mul_tw(v, A.scale);
+          fe_store(dst + K, v);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        uint32_t ph = sm_phys(pos0 + (uint32_t)m * S);
+#pragma unroll
+        for (int l = 0; l < 8; ++l) sm[l * T + ph] = x[m].v[l];
+      }
+    }
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(512, 1) ntt_pass_kernel(const NttPass A, const F f) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t T = 1u << A.logT;
+  const uint32_t xb = blockIdx.x;
+  const uint32_t Jcta = ((xb & ((1u << A.nl) - 1u)) << A.sl) | ((xb >> A.nl) << A.sh);
+  const uint32_t col0 = A.c_is_col ? (blockIdx.y << A.logC) : blockIdx.y;
+  int a = A.k;
+  for (int rd = 0; rd < A.nrounds; ++rd) {
+    const int r = A.r[rd];
+    a -= r;
+    const bool first = rd == 0, last = rd == A.nrounds - 1;
+    if (r == 3) ntt_round<F, 3>(A, f, sm, T, Jcta, col0, a, first, last);
+    else if (r == 2) ntt_round<F, 2>(A, f, sm, T, Jcta, col0, a, first, last);
+    else ntt_round<F, 1>(A, f, sm, T, Jcta, col0, a, first, last);
+    if (!last) __syncthreads();
+  }
+}
+
+// W[m + i] = W[i] * wm  for i < m  (table doubling; both operands in twiddle form)
+template <class F>
+__global__ void twiddle_extend_kernel(fe* W, unsigned long long m, unsigned long long total, fe wm, const F f) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i < m && m + i < total) fe_store(W + m + i, f.mul_tw(fe_load(W + i), wm));
+}
+
+}  // namespace stk

@@ -1,0 +1,490 @@
+// ntt_api.cu -- context, twiddle tables, NTT plans and the NTT entry points of the C ABI.
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include "ctx.h"
+#include "ntt.cuh"
+
+using namespace stk;
+
+// ------------------------------------------------------------------ small helpers
+
+fe stk_load_fe(const uint32_t* w) {
+  fe r;
+  for (int i = 0; i < 8; ++i) r.v[i] = w[i];
+  return r;
+}
+fe stk_h_mul(stk_ctx* c, const fe& a, const fe& b) { return host::mulmod(a, b, c->p); }
+fe stk_h_pow(stk_ctx* c, const fe& a, uint64_t e) { return host::pow_u64(a, e, c->p); }
+fe stk_h_inv(stk_ctx* c, const fe& a) { return host::invmod(a, c->p); }
+fe stk_h_to_tw(stk_ctx* c, const fe& a) { return c->is_stark ? a : host::mulmod(a, c->mont.rone, c->p); }
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+int stk_scratch(stk_ctx* c, int slot, uint64_t bytes, void** out) {
+  if (c->scratch_bytes[slot] < bytes) {
+    if (c->scratch[slot]) {
+      STK_CUDA(c, cudaStreamSynchronize(c->stream));
+      STK_CUDA(c, cudaFree(c->scratch[slot]));
+      c->scratch[slot] = nullptr;
+      c->scratch_bytes[slot] = 0;
+    }
+    STK_CUDA(c, cudaMalloc(&c->scratch[slot], bytes));
+    c->scratch_bytes[slot] = bytes;
+  }
+  *out = c->scratch[slot];
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ context
+
+extern "C" __attribute__((visibility("default"))) int stk_version(void) { return 1; }
+
+extern "C" __attribute__((visibility("default"))) int stk_init(int device, stk_ctx** out) {
+  if (!out) return STK_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return STK_ECUDA;
+  stk_ctx* c = new stk_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return STK_ECUDA; }
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return STK_ECUDA; }
+  c->stream = c->own_stream;
+  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  c->is_stark = true;
+  c->p = StarkField::modulus();
+  *out = c;
+  return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void stk_destroy(stk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& t : c->tables) cudaFree(t.d);
+  for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; ++i) if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" __attribute__((visibility("default"))) const char* stk_last_error(stk_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+extern "C" __attribute__((visibility("default"))) int stk_set_stream(stk_ctx* c, void* s) {
+  if (!c) return STK_EINVAL;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_sync(stk_ctx* c) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_field_set(stk_ctx* c, const uint32_t p32[8]) {
+  if (!c || !p32) return STK_EINVAL;
+  fe p = stk_load_fe(p32);
+  if (fe_eq(p, c->p)) return STK_OK;
+  // tables are per field: drop them
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& t : c->tables) cudaFree(t.d);
+  c->tables.clear();
+  if (host::is_stark_prime(p)) {
+    c->is_stark = true;
+    c->p = p;
+    return STK_OK;
+  }
+  MontField F;
+  if (!host::mont_setup(&F, p)) return stk_fail(c, STK_EUNSUPPORTED, "modulus must be odd and > 1");
+  c->mont = F;
+  c->is_stark = false;
+  c->p = p;
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ memory helpers
+
+extern "C" __attribute__((visibility("default"))) int stk_dev_alloc(stk_ctx* c, uint64_t bytes, void** d) {
+  if (!c || !d) return STK_EINVAL;
+  STK_CUDA(c, cudaMalloc(d, bytes ? bytes : 1));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_dev_free(stk_ctx* c, void* d) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  STK_CUDA(c, cudaFree(d));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_host_alloc(stk_ctx* c, uint64_t bytes, void** h) {
+  if (!c || !h) return STK_EINVAL;
+  STK_CUDA(c, cudaHostAlloc(h, bytes ? bytes : 1, cudaHostAllocDefault));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_host_free(stk_ctx* c, void* h) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaFreeHost(h));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_memcpy_h2d(stk_ctx* c, void* d, const void* h, uint64_t bytes) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_memcpy_d2h(stk_ctx* c, void* h, const void* d, uint64_t bytes) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_memcpy_d2d(stk_ctx* c, void* dd, const void* ds, uint64_t bytes) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaMemcpyAsync(dd, ds, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return STK_OK;
+}
+extern "C" __attribute__((visibility("default"))) int stk_memset(stk_ctx* c, void* d, int value, uint64_t bytes) {
+  if (!c) return STK_EINVAL;
+  STK_CUDA(c, cudaMemsetAsync(d, value, bytes, c->stream));
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ twiddle tables
+
+int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
+  for (auto& t : c->tables)
+    if (t.n == n && fe_eq(t.root, root)) { *d_table = t.d; return STK_OK; }
+  if (c->tables.size() >= 24) {  // bounded cache: drop the oldest
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->tables.front().d);
+    c->tables.erase(c->tables.begin());
+  }
+  stk_table t;
+  t.root = root; t.n = n; t.mont = !c->is_stark; t.d = nullptr;
+  STK_CUDA(c, cudaMalloc(&t.d, std::max<uint64_t>(n, 1) * sizeof(fe)));
+  fe one = stk_h_to_tw(c, host::reduce(host::from_u64(1), c->p));
+  STK_CUDA(c, cudaMemcpyAsync(t.d, &one, sizeof(fe), cudaMemcpyHostToDevice, c->stream));
+  fe wm = root;  // root^m, plain
+  for (uint64_t m = 1; m < n; m <<= 1) {
+    fe wm_tw = stk_h_to_tw(c, wm);
+    uint64_t cnt = std::min<uint64_t>(m, n - m);
+    unsigned blocks = (unsigned)((cnt + 255) / 256);
+    if (c->is_stark) twiddle_extend_kernel<StarkField><<<blocks, 256, 0, c->stream>>>(t.d, m, n, wm_tw, StarkField());
+    else twiddle_extend_kernel<MontField><<<blocks, 256, 0, c->stream>>>(t.d, m, n, wm_tw, c->mont);
+    wm = stk_h_mul(c, wm, wm);
+  }
+  STK_CUDA(c, cudaGetLastError());
+  c->tables.push_back(t);
+  *d_table = t.d;
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ NTT plan
+
+static int ilog2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) ++l; return l; }
+
+static void fill_rounds(NttPass& P) {
+  int k = P.k, rem = k % 3, idx = 0;
+  if (rem) P.r[idx++] = rem;
+  for (int i = 0; i < k / 3; ++i) P.r[idx++] = 3;
+  P.nrounds = idx;
+}
+
+// Cuts the n index bits into passes (top bits first) and fixes each pass's tile geometry.
+static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
+  const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 12)));
+  const int kmax = std::min(logT, std::max(3, env_int("STK_NTT_KMAX", 11)));
+  plan.clear();
+  if (n <= kmax) {
+    NttPass P;
+    memset(&P, 0, sizeof P);
+    P.n = n; P.lo = 0; P.k = n;
+    P.logC = std::min(logT - n, ilog2_u64(batch));
+    P.logT = P.k + P.logC;
+    P.c_is_col = 1; P.cb = 0; P.nl = 0; P.sl = 0; P.sh = 0;
+    P.final_pass = 1;
+    fill_rounds(P);
+    plan.push_back(P);
+    return STK_OK;
+  }
+  int npass = (n + kmax - 1) / kmax;
+  int hi = n;
+  for (int i = 0; i < npass; ++i) {
+    int k = (hi + (npass - i) - 1) / (npass - i);  // spread the remaining bits evenly
+    NttPass P;
+    memset(&P, 0, sizeof P);
+    P.n = n; P.k = k; P.lo = hi - k;
+    P.final_pass = (i == npass - 1);
+    P.c_is_col = 0;
+    P.logC = logT - k;
+    if (!P.final_pass) {
+      if (P.logC > P.lo) P.logC = P.lo;
+      P.cb = 0;
+      P.nl = P.lo - P.logC; P.sl = P.logC; P.sh = P.lo + P.k;
+    } else {
+      if (P.logC > n - k) P.logC = n - k;
+      P.cb = n - P.logC;
+      P.nl = n - P.logC - k; P.sl = k; P.sh = 0;
+    }
+    P.logT = P.k + P.logC;
+    fill_rounds(P);
+    plan.push_back(P);
+    hi -= k;
+  }
+  return STK_OK;
+}
+
+template <class F>
+static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const uint32_t T = 1u << P.logT;
+  unsigned threads = std::max(1u, T >> 3);
+  uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
+  uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
+  if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
+  dim3 grid((unsigned)tiles, (unsigned)cols);
+  size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
+  ntt_pass_kernel<F><<<grid, threads, smem, s>>>(P, f);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+// direct DFT for orders that are not a power of two >= 8 (_simple_ft, starks/fft.py:287-300)
+template <class F>
+__global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stride, fe* out, uint64_t out_stride,
+                                   uint64_t n, uint64_t batch, const fe* W, int do_scale, fe scale, const F f) {
+  uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * batch) return;
+  uint64_t k = idx % n, col = idx / n;
+  const fe* src = in + col * in_stride;
+  fe acc = fe_zero();
+  for (uint64_t j = 0; j < n_in; ++j) {
+    uint64_t e = (j * k) % n;
+    acc = f.add(acc, f.mul_tw(fe_load(src + j), fe_load_ro(W + e)));
+  }
+  if (do_scale) acc = f.mul_tw(acc, scale);
+  fe_store(out + col * out_stride + k, acc);
+}
+
+static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_in, uint64_t n_in, uint64_t in_stride,
+                      fe* d_out, uint64_t out_stride, uint64_t n, uint64_t batch, const fe& root, int inverse,
+                      int scale) {
+  if (n == 0 || batch == 0) return STK_OK;
+  if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
+                                (unsigned long long)n_in, (unsigned long long)n);
+  if (n > (1ull << 30)) return stk_fail(c, STK_EUNSUPPORTED, "transform length above 2^30");
+  fe one = host::reduce(host::from_u64(1), c->p);
+  fe rn = stk_h_pow(c, root, n);
+  if (!fe_eq(rn, one)) return stk_fail(c, STK_EINVAL, "root^n != 1: n is not the order of the root");
+  if (n % 2 == 0 && n > 1) {
+    fe rh = stk_h_pow(c, root, n / 2);
+    if (fe_eq(rh, one)) return stk_fail(c, STK_EINVAL, "root has order below n");
+  }
+  fe w = inverse ? stk_h_inv(c, root) : root;
+  const fe* W = nullptr;
+  STK_TRY(stk_get_table(c, w, n, &W));
+  fe scale_tw = fe_zero();
+  int do_scale = inverse && scale;
+  if (do_scale) {
+    fe nn = host::reduce(host::from_u64(n), c->p);
+    scale_tw = stk_h_to_tw(c, stk_h_inv(c, nn));
+  }
+  bool pow2 = (n & (n - 1)) == 0;
+  if (!pow2 || n < 8) {
+    if (n > 4096) return stk_fail(c, STK_EUNSUPPORTED, "non power-of-two order above 4096");
+    uint64_t total = n * batch;
+    unsigned blocks = (unsigned)((total + 127) / 128);
+    const fe* src = d_in;
+    if ((const void*)d_in == (const void*)d_out) {  // every output reads the whole column
+      void* tmp;
+      STK_TRY(stk_scratch(c, scratch_slot, batch * n_in * sizeof(fe), &tmp));
+      for (uint64_t b = 0; b < batch; ++b)
+        STK_CUDA(c, cudaMemcpyAsync((fe*)tmp + b * n_in, d_in + b * in_stride, n_in * sizeof(fe),
+                                    cudaMemcpyDeviceToDevice, s));
+      src = (const fe*)tmp;
+      in_stride = n_in;
+    }
+    if (c->is_stark)
+      dft_generic_kernel<StarkField><<<blocks, 128, 0, s>>>(src, n_in, in_stride, d_out, out_stride, n, batch, W,
+                                                           do_scale, scale_tw, StarkField());
+    else
+      dft_generic_kernel<MontField><<<blocks, 128, 0, s>>>(src, n_in, in_stride, d_out, out_stride, n, batch, W,
+                                                          do_scale, scale_tw, c->mont);
+    STK_CUDA(c, cudaGetLastError());
+    return STK_OK;
+  }
+  int logn = ilog2_u64(n);
+  std::vector<NttPass> plan;
+  STK_TRY(build_plan(logn, batch, plan));
+  fe* tmp = nullptr;
+  bool need_tmp = plan.size() > 1 || (const void*)d_in == (const void*)d_out;
+  if (need_tmp) {
+    void* t;
+    STK_TRY(stk_scratch(c, scratch_slot, batch * n * sizeof(fe), &t));
+    tmp = (fe*)t;
+  }
+  for (size_t i = 0; i < plan.size(); ++i) {
+    NttPass& P = plan[i];
+    P.batch = (uint32_t)batch;
+    P.W = W;
+    P.do_scale = (P.final_pass && do_scale) ? 1 : 0;
+    P.scale = scale_tw;
+    if (plan.size() == 1) {
+      if (need_tmp) {  // in place: stage the input
+        for (uint64_t b = 0; b < batch; ++b)
+          STK_CUDA(c, cudaMemcpyAsync(tmp + b * n, d_in + b * in_stride, n_in * sizeof(fe),
+                                      cudaMemcpyDeviceToDevice, s));
+        P.in = tmp; P.in_col_stride = n;
+      } else {
+        P.in = d_in; P.in_col_stride = in_stride;
+      }
+      P.n_in = (uint32_t)n_in;
+      P.out = d_out; P.out_col_stride = out_stride;
+    } else if (i == 0) {
+      P.in = d_in; P.in_col_stride = in_stride; P.n_in = (uint32_t)n_in;
+      P.out = tmp; P.out_col_stride = n;
+    } else if (!P.final_pass) {
+      P.in = tmp; P.in_col_stride = n; P.n_in = (uint32_t)n;
+      P.out = tmp; P.out_col_stride = n;
+    } else {
+      P.in = tmp; P.in_col_stride = n; P.n_in = (uint32_t)n;
+      P.out = d_out; P.out_col_stride = out_stride;
+    }
+    if (c->is_stark) STK_TRY(launch_pass<StarkField>(c, s, P, StarkField()));
+    else STK_TRY(launch_pass<MontField>(c, s, P, c->mont));
+  }
+  return STK_OK;
+}
+
+int stk_ntt_dev(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, fe* d_out, uint64_t out_stride,
+                uint64_t n, uint64_t batch, const fe& root, int inverse, int scale) {
+  return ntt_dev_on(c, c->stream, 0, d_in, n_in, in_stride, d_out, out_stride, n, batch, root, inverse, scale);
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_ntt(stk_ctx* c, const uint32_t* d_in, uint64_t n_in, uint64_t in_stride, uint32_t* d_out,
+                       uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse) {
+  if (!c || !d_out || !root || (!d_in && n_in)) return STK_EINVAL;
+  return stk_ntt_dev(c, (const fe*)d_in, n_in, in_stride, (fe*)d_out, out_stride, n, batch, stk_load_fe(root),
+                     inverse, 1);
+}
+
+// Host buffers: columns stream through two device slots; H2D of chunk i+1 and D2H of chunk
+// i-1 overlap the transform of chunk i (separate streams, events for ordering).
+extern "C" __attribute__((visibility("default"))) int stk_ntt_host(stk_ctx* c, const uint32_t* h_in, uint64_t n_in, uint64_t in_stride, uint32_t* h_out,
+                            uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse) {
+  if (!c || !h_out || !root || (!h_in && n_in)) return STK_EINVAL;
+  if (n_in > n) return stk_fail(c, STK_EINDEX, "input length exceeds the order of the root");
+  if (n == 0 || batch == 0) return STK_OK;
+  fe r = stk_load_fe(root);
+  const uint64_t col_bytes = n * sizeof(fe);
+  uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / col_bytes);
+  chunk = std::min(chunk, batch);
+  if (batch > chunk && batch < 2 * chunk) chunk = (batch + 1) / 2;
+  // slot buffers: in (n_in per col, packed) and out (n per col)
+  void* bufs;
+  const uint64_t in_b = chunk * std::max<uint64_t>(n_in, 1) * sizeof(fe), out_b = chunk * col_bytes;
+  STK_TRY(stk_scratch(c, 3, 2 * (in_b + out_b), &bufs));
+  char* base = (char*)bufs;
+  fe* din[2] = {(fe*)base, (fe*)(base + in_b)};
+  fe* dout[2] = {(fe*)(base + 2 * in_b), (fe*)(base + 2 * in_b + out_b)};
+  // make sure tables exist before the streams fork (built on c->stream)
+  {
+    const fe* W;
+    fe w = inverse ? stk_h_inv(c, r) : r;
+    STK_TRY(stk_get_table(c, w, n, &W));
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int slot = 0;
+  for (uint64_t b0 = 0; b0 < batch; b0 += chunk, slot ^= 1) {
+    uint64_t nb = std::min(chunk, batch - b0);
+    cudaStream_t s = c->copy_streams[slot];
+    if (n_in) {
+      if (in_stride == n_in)
+        STK_CUDA(c, cudaMemcpyAsync(din[slot], h_in + b0 * in_stride * 8, nb * n_in * sizeof(fe),
+                                    cudaMemcpyHostToDevice, s));
+      else
+        STK_CUDA(c, cudaMemcpy2DAsync(din[slot], n_in * sizeof(fe), h_in + b0 * in_stride * 8,
+                                      in_stride * sizeof(fe), n_in * sizeof(fe), nb, cudaMemcpyHostToDevice, s));
+    }
+    STK_TRY(ntt_dev_on(c, s, 1 + slot, din[slot], n_in, n_in, dout[slot], n, n, nb, r, inverse, 1));
+    if (out_stride == n)
+      STK_CUDA(c, cudaMemcpyAsync(h_out + b0 * out_stride * 8, dout[slot], nb * col_bytes, cudaMemcpyDeviceToHost, s));
+    else
+      STK_CUDA(c, cudaMemcpy2DAsync(h_out + b0 * out_stride * 8, out_stride * sizeof(fe), dout[slot], col_bytes,
+                                    col_bytes, nb, cudaMemcpyDeviceToHost, s));
+  }
+  STK_CUDA(c, cudaStreamSynchronize(c->copy_streams[0]));
+  STK_CUDA(c, cudaStreamSynchronize(c->copy_streams[1]));
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ pointwise helpers
+
+template <class F>
+__global__ void vec_op_kernel(int op, const fe* a, const fe* b, fe* out, uint64_t n, const F f) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe x = fe_load(a + i), y = fe_load(b + i), r;
+  if (op == 0) r = f.add(x, y);
+  else if (op == 1) r = f.sub(x, y);
+  else r = f_mul(f, x, y);
+  fe_store(out + i, r);
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_vec_op(stk_ctx* c, int op, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, uint64_t n) {
+  if (!c || op < 0 || op > 2) return STK_EINVAL;
+  if (!n) return STK_OK;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (c->is_stark) vec_op_kernel<StarkField><<<blocks, 256, 0, c->stream>>>(op, (const fe*)d_a, (const fe*)d_b, (fe*)d_out, n, StarkField());
+  else vec_op_kernel<MontField><<<blocks, 256, 0, c->stream>>>(op, (const fe*)d_a, (const fe*)d_b, (fe*)d_out, n, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_mul_polys(stk_ctx* c, const uint32_t* d_a, uint64_t na, const uint32_t* d_b, uint64_t nb,
+                             uint32_t* d_out, uint64_t n, const uint32_t root[8]) {
+  if (!c || !d_out || !root) return STK_EINVAL;
+  if (na > n || nb > n) return stk_fail(c, STK_EINDEX, "operand longer than the order of the root");
+  fe r = stk_load_fe(root);
+  void* t;
+  STK_TRY(stk_scratch(c, 2, 2 * n * sizeof(fe), &t));
+  fe* x1 = (fe*)t;
+  fe* x2 = x1 + n;
+  STK_TRY(stk_ntt_dev(c, (const fe*)d_a, na, na, x1, n, n, 1, r, 0, 0));
+  STK_TRY(stk_ntt_dev(c, (const fe*)d_b, nb, nb, x2, n, n, 1, r, 0, 0));
+  STK_TRY(stk_vec_op(c, 2, (const uint32_t*)x1, (const uint32_t*)x2, (uint32_t*)x1, n));
+  // _fft(..., rootz[:0:-1]) without the 1/n factor (starks/fft.py:345)
+  STK_TRY(stk_ntt_dev(c, x1, n, n, (fe*)d_out, n, n, 1, r, 1, 0));
+  return STK_OK;
+}
+
+template <class F>
+__global__ void from_tw_kernel(const fe* W, fe* out, uint64_t n, const F f) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) fe_store(out + i, f.from_tw(fe_load(W + i)));
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_power_cycle(stk_ctx* c, const uint32_t r32[8], uint64_t n, uint32_t* d_out) {
+  if (!c || !r32 || !d_out) return STK_EINVAL;
+  if (!n) return STK_OK;
+  const fe* W;
+  STK_TRY(stk_get_table(c, stk_load_fe(r32), n, &W));
+  if (c->is_stark) {
+    STK_CUDA(c, cudaMemcpyAsync(d_out, W, n * sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    from_tw_kernel<MontField><<<blocks, 256, 0, c->stream>>>(W, (fe*)d_out, n, c->mont);
+    STK_CUDA(c, cudaGetLastError());
+  }
+  return STK_OK;
+}

@@ -1,0 +1,179 @@
+"""Engine: one libstarks_b200 context (one GPU, one stream) with numpy-facing helpers.
+
+Host code above the C ABI.  Device memory is owned either by the library
+(`Engine.alloc`) or by torch tensors whose `data_ptr()` is passed straight through;
+nothing here computes on the CPU."""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from .limbs import int_to_limbs
+
+P_STARK = 2**256 - 351 * 2**32 + 1
+
+
+class DevBuf:
+  """A device allocation made through stk_dev_alloc."""
+
+  def __init__(self, eng, nbytes):
+    self.eng, self.nbytes = eng, int(nbytes)
+    p = ctypes.c_void_p()
+    eng._check(eng.lib.stk_dev_alloc(eng.ctx, self.nbytes, ctypes.byref(p)))
+    self.ptr = p.value
+
+  def free(self):
+    if self.ptr is not None and self.eng.ctx is not None:
+      self.eng.lib.stk_dev_free(self.eng.ctx, self.ptr)
+    self.ptr = None
+
+  def __del__(self):
+    try:
+      self.free()
+    except Exception:
+      pass
+
+  def at(self, byte_offset):
+    return self.ptr + int(byte_offset)
+
+  def upload(self, arr, byte_offset=0):
+    arr = np.ascontiguousarray(arr)
+    assert byte_offset + arr.nbytes <= self.nbytes
+    self.eng._check(self.eng.lib.stk_memcpy_h2d(self.eng.ctx, self.ptr + byte_offset, arr.ctypes.data, arr.nbytes))
+    self.eng.sync()  # pageable source: keep it alive until the copy is done
+    return self
+
+  def download(self, shape, dtype=np.uint32, byte_offset=0):
+    out = np.empty(shape, dtype=dtype)
+    assert byte_offset + out.nbytes <= self.nbytes, (byte_offset, out.nbytes, self.nbytes)
+    self.eng._check(self.eng.lib.stk_memcpy_d2h(self.eng.ctx, out.ctypes.data, self.ptr + byte_offset, out.nbytes))
+    return out
+
+
+class PinnedBuf:
+  """Pinned host memory (stk_host_alloc) exposed as a numpy array."""
+
+  def __init__(self, eng, shape, dtype=np.uint32):
+    self.eng = eng
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    eng._check(eng.lib.stk_host_alloc(eng.ctx, n, ctypes.byref(p)))
+    self.ptr = p.value
+    buf = (ctypes.c_uint8 * n).from_address(self.ptr)
+    self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+  def free(self):
+    if self.ptr is not None:
+      self.array = None
+      self.eng.lib.stk_host_free(self.eng.ctx, self.ptr)
+      self.ptr = None
+
+
+class Engine:
+  """Owns a stk_ctx.  Raises if the library is not built or no CUDA device exists."""
+
+  def __init__(self, device=0):
+    self.lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    rc = self.lib.stk_init(int(device), ctypes.byref(ctx))
+    if rc != 0:
+      self.ctx = None
+      raise _lib.StarksB200Error(
+          "stk_init(device=%d) failed (rc=%d): a CUDA device is required; there is no CPU fallback" % (device, rc))
+    self.ctx = ctx
+    self.device = device
+    self.p = P_STARK
+
+  def close(self):
+    if self.ctx is not None:
+      self.lib.stk_destroy(self.ctx)
+      self.ctx = None
+
+  def _check(self, rc):
+    if rc == 0:
+      return
+    msg = self.lib.stk_last_error(self.ctx).decode() if self.ctx else ""
+    if rc == _lib.STK_EINDEX:
+      raise IndexError(msg or "list index out of range")
+    if rc == _lib.STK_EINVAL:
+      raise ValueError(msg or "invalid argument")
+    raise _lib.StarksB200Error("libstarks_b200 error %d: %s" % (rc, msg))
+
+  # ---- context ---------------------------------------------------------------
+  def set_field(self, p):
+    p = int(p)
+    if p != self.p:
+      self._check(self.lib.stk_field_set(self.ctx, _u32(int_to_limbs(p))))
+      self.p = p
+
+  def set_stream(self, cuda_stream_handle):
+    self._check(self.lib.stk_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+  def sync(self):
+    self._check(self.lib.stk_sync(self.ctx))
+
+  def alloc(self, nbytes):
+    return DevBuf(self, nbytes)
+
+  def pinned(self, shape, dtype=np.uint32):
+    return PinnedBuf(self, shape, dtype)
+
+  # ---- NTT -------------------------------------------------------------------
+  def ntt(self, d_in, n_in, in_stride, d_out, out_stride, n, batch, root, inverse=False):
+    """Device pointers (ints); see stk_ntt."""
+    self._check(self.lib.stk_ntt(self.ctx, d_in, n_in, in_stride, d_out, out_stride, n, batch,
+                                 _u32(int_to_limbs(int(root) % self.p)), int(bool(inverse))))
+
+  def ntt_host(self, cols, n, root, inverse=False, out=None):
+    """cols: (batch, n_in, 8) uint32 host array -> (batch, n, 8) uint32 (stk_ntt_host)."""
+    cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    batch, n_in, _ = cols.shape
+    if out is None:
+      out = np.empty((batch, n, 8), dtype=np.uint32)
+    self._check(self.lib.stk_ntt_host(self.ctx, cols.ctypes.data, n_in, n_in, out.ctypes.data, n, n, batch,
+                                      _u32(int_to_limbs(int(root) % self.p)), int(bool(inverse))))
+    return out
+
+  def mul_polys(self, a, b, n, root):
+    a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 8)
+    b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 8)
+    da, db, do = self.alloc(max(a.nbytes, 32)), self.alloc(max(b.nbytes, 32)), self.alloc(n * 32)
+    da.upload(a)
+    db.upload(b)
+    self._check(self.lib.stk_mul_polys(self.ctx, da.ptr, len(a), db.ptr, len(b), do.ptr, n,
+                                       _u32(int_to_limbs(int(root) % self.p))))
+    out = do.download((n, 8))
+    for x in (da, db, do):
+      x.free()
+    return out
+
+  def power_cycle(self, r, n):
+    do = self.alloc(n * 32)
+    self._check(self.lib.stk_power_cycle(self.ctx, _u32(int_to_limbs(int(r) % self.p)), n, do.ptr))
+    out = do.download((n, 8))
+    do.free()
+    return out
+
+  def microbench(self, which, iters):
+    ms, ops = ctypes.c_float(), ctypes.c_double()
+    self._check(self.lib.stk_microbench(self.ctx, which, iters, ctypes.byref(ms), ctypes.byref(ops)))
+    return ms.value, ops.value
+
+
+def _u32(arr):
+  return arr.ctypes.data_as(_lib.u32p)
+
+
+_default = None
+_lock = threading.Lock()
+
+
+def default_engine() -> Engine:
+  """Process-wide engine on LOCAL_RANK's GPU (one process per GPU)."""
+  global _default
+  with _lock:
+    if _default is None:
+      import os
+      _default = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
