@@ -85,6 +85,47 @@ int stk_vec_op(stk_ctx* ctx, int op, const uint32_t* d_a, const uint32_t* d_b, u
 /* get_power_cycle (starks/utils.py:30-38): out[i] = r^i, i < n (n = order of r). */
 int stk_power_cycle(stk_ctx* ctx, const uint32_t r[8], uint64_t n, uint32_t* d_out);
 
+/* ---- LDE ------------------------------------------------------------------------ */
+/* construct_trace_polynomials + evaluation loop (starks/stark.py:27-36, 254-256): per column
+ * inverse NTT of `steps` trace values over <G1>, G1 = g2^ext, then forward NTT of the
+ * coefficients over <g2> (order steps*ext).  d_coeffs may be NULL (scratch is used). */
+int stk_lde(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+            uint64_t cols, const uint32_t g2[8], uint32_t* d_coeffs, uint64_t coeff_stride, uint32_t* d_evals,
+            uint64_t eval_stride);
+/* stk_lde followed by stk_merkle_commit over the extended columns (stark.py:254-257). */
+int stk_lde_commit(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                   uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride, uint8_t* d_nodes,
+                   uint8_t* h_root);
+
+/* ---- Merkle ---------------------------------------------------------------------- */
+/* merkelize_polynomial_evaluations + merkelize (starks/merkle_tree.py:36-56, 94-119) over
+ * `ncols` device columns of n rows (n a power of two >= 4): leaf(row) = concatenation of the
+ * columns' 32-byte big-endian values, leaves in permute4 order (:11-23), unhashed; node i =
+ * BLAKE2s(node 2i || node 2i+1).  d_nodes receives 32*n bytes (node i at byte 32*i, i in
+ * [1, n); entry 0 zero).  h_root (optional) receives node 1.  One column gives
+ * merkelize(values). */
+int stk_merkle_commit(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                      uint8_t* d_nodes, uint8_t* h_root);
+/* merkelize (merkle_tree.py:36-56) over n raw leaves of leaf_len bytes in ORIGINAL order;
+ * any n >= 4 (the heap formula is applied as is, e.g. n = 144 in test_merkle_tree.py:32-38;
+ * n mod 4 trailing leaves are dropped exactly as permute4 does). */
+int stk_merkle_commit_raw(stk_ctx* ctx, const uint8_t* d_leaves, uint64_t n, uint64_t leaf_len, uint8_t* d_nodes,
+                          uint8_t* h_root);
+/* mk_branch (merkle_tree.py:59-68) for k original indices of a column tree.  Record per
+ * query (rec_bytes each, host memory): leaf (32*ncols) | sibling leaf (32*ncols) | sibling
+ * nodes bottom-up (32 bytes each, log2(n)-1 of them). */
+int stk_merkle_paths(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                     const uint8_t* d_nodes, const uint64_t* h_indices, uint64_t k, uint8_t* h_out,
+                     uint64_t rec_bytes);
+
+/* ---- FRI ------------------------------------------------------------------------- */
+/* The `column` of one FRI layer (starks/fri.py:236-242; multi_interp_4,
+ * starks/poly_utils.py:412-440): out[i], i < n/4, is the degree<4 interpolant through
+ * (root^(i+jn/4), vals[i+jn/4]), j<4, evaluated at special_x (any 256-bit integer; the
+ * reference does not reduce it, fri.py:229). */
+int stk_fri_fold4(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, const uint32_t root[8],
+                  const uint32_t special_x[8], uint32_t* d_out);
+
 /* ---- K0: integer-pipe microbenchmarks (roofline denominators) ---------------------- */
 /* which: 0 IMAD, 1 IMAD.WIDE, 2 IADD3, 3 IMAD.HI, 4 IADD3+LOP3+SHF (BLAKE2s mix),
  * 5 field multiply, 6 NTT butterfly, 7 IMAD+IADD3, 8 IMAD.WIDE+IADD3, 9 carry-chain adds,

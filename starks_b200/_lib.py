@@ -46,6 +46,12 @@ SIGNATURES = {
     "stk_mul_polys": (cint, [vp, vp, u64, vp, u64, vp, u64, u32p]),
     "stk_vec_op": (cint, [vp, cint, vp, vp, vp, u64]),
     "stk_power_cycle": (cint, [vp, u32p, u64, vp]),
+    "stk_lde": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, u64]),
+    "stk_lde_commit": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, vp]),
+    "stk_merkle_commit": (cint, [vp, vp, u64, u64, u64, vp, vp]),
+    "stk_merkle_commit_raw": (cint, [vp, vp, u64, u64, vp, vp]),
+    "stk_merkle_paths": (cint, [vp, vp, u64, u64, u64, vp, vp, u64, vp, u64]),
+    "stk_fri_fold4": (cint, [vp, vp, u64, u32p, u32p, vp]),
     "stk_microbench": (cint, [vp, cint, u64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -187,17 +187,12 @@ struct StarkField {
     const uint32_t* L = T;
     const uint32_t* H = T + 8;
     // fold 1:  L + H*2^256 = L + (351*H << 32) - H
-    uint32_t U[9];
-    {
-      uint32_t carry = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint64_t t = (uint64_t)H[i] * 351u + carry;
-        U[i] = (uint32_t)t;
-        carry = (uint32_t)(t >> 32);
-      }
-      U[8] = carry;
-    }
+    // U = 351*H (9 limbs): even limbs of H give four non-overlapping 41-bit products,
+    // the odd ones are accumulated one limb up in a single carry chain.
+    uint32_t U[10];
+    U[8] = 0;
+    mul_row_first(U, H, 351u);
+    mad_row(U + 1, H + 1, 351u);
     uint32_t B[10];
     B[0] = L[0];
     asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(B[1]) : "r"(L[1]), "r"(U[0]));

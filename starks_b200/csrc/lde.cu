@@ -1,0 +1,41 @@
+// lde.cu -- low-degree extension of trace columns and the LDE -> Merkle commit pipeline.
+// Replaces construct_trace_polynomials (starks/stark.py:27-36: inverse NTT of each witness
+// column over <G1>) followed by the evaluation loop of mk_proof (starks/stark.py:254-256:
+// forward NTT over <G2>, G1 = G2^ext) and merkelize_polynomial_evaluations (:257).  There is
+// no coset shift in the reference: the evaluation domain is the subgroup <G2> itself, so
+// evals[i*ext] == trace[i].
+#include "ctx.h"
+
+using namespace stk;
+
+#define STK_API extern "C" __attribute__((visibility("default")))
+
+extern "C" int stk_merkle_commit(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                                 uint8_t* d_nodes, uint8_t* h_root);
+
+// Coefficients (optional output, cols x steps) and evaluations (cols x steps*ext).
+STK_API int stk_lde(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                    uint64_t cols, const uint32_t g2[8], uint32_t* d_coeffs, uint64_t coeff_stride, uint32_t* d_evals,
+                    uint64_t eval_stride) {
+  if (!c || !d_trace || !d_evals || !g2 || steps == 0 || ext == 0 || cols == 0) return STK_EINVAL;
+  const uint64_t n = steps * ext;
+  fe G2 = stk_load_fe(g2);
+  fe G1 = stk_h_pow(c, G2, ext);
+  fe* coef = (fe*)d_coeffs;
+  if (!coef) {
+    void* t;
+    STK_TRY(stk_scratch(c, 1, cols * steps * sizeof(fe), &t));
+    coef = (fe*)t;
+    coeff_stride = steps;
+  }
+  STK_TRY(stk_ntt_dev(c, (const fe*)d_trace, steps, trace_stride, coef, coeff_stride, steps, cols, G1, 1, 1));
+  STK_TRY(stk_ntt_dev(c, coef, steps, coeff_stride, (fe*)d_evals, eval_stride, n, cols, G2, 0, 0));
+  return STK_OK;
+}
+
+STK_API int stk_lde_commit(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                           uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride,
+                           uint8_t* d_nodes, uint8_t* h_root) {
+  STK_TRY(stk_lde(c, d_trace, steps, trace_stride, ext, cols, g2, nullptr, 0, d_evals, eval_stride));
+  return stk_merkle_commit(c, d_evals, steps * ext, cols, eval_stride, d_nodes, h_root);
+}

@@ -1,0 +1,236 @@
+// merkle.cu -- BLAKE2s Merkle commitment over evaluation columns, level-by-level reduction
+// and branch extraction.  Replaces merkelize / permute4 / merkelize_polynomial_evaluations /
+// mk_branch of starks/merkle_tree.py:11-68, 94-119.
+//
+// Tree layout (identical to the reference's list): heap order, root at index 1, internal
+// node i = BLAKE2s(node 2i || node 2i+1), leaves (NOT hashed) at indices [n, 2n) in
+// permute4 order: leaf position l holds original row (l mod 4) * n/4 + l div 4.  On the
+// device only the n internal nodes are stored (32 bytes each, entry 0 unused); leaves stay
+// where they are -- in the evaluation columns -- and are serialised on the fly:
+// leaf(row) = concat over columns of the 32-byte big-endian value (merkle_tree.py:116-118).
+#include <algorithm>
+#include "blake2s.cuh"
+#include "ctx.h"
+
+using namespace stk;
+
+namespace {
+
+// Bottom level over column leaves.  One thread per node i in [n/2, n): hashes
+// leaf(2i-n) || leaf(2i-n+1) = 2*ncols values = ncols 64-byte blocks.
+__global__ void __launch_bounds__(256) merkle_leaf_pairs_cols_kernel(const fe* __restrict__ cols, uint64_t n,
+                                                                      uint32_t ncols, uint64_t col_stride,
+                                                                      uint32_t* __restrict__ nodes) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t half = n >> 1, q = n >> 2;
+  if (i >= half) return;
+  const uint64_t l0 = 2 * i;
+  const uint64_t x0 = (l0 & 3) * q + (l0 >> 2), x1 = x0 + q;
+  uint32_t h[8];
+  b2s_init(h);
+  const uint32_t nblk = ncols;  // 2*ncols values, two per block
+  for (uint32_t b = 0; b < nblk; ++b) {
+    uint32_t m[16];
+#pragma unroll
+    for (int half_blk = 0; half_blk < 2; ++half_blk) {
+      uint32_t s = 2 * b + half_blk;
+      const fe* src = (s < ncols) ? (cols + (uint64_t)s * col_stride + x0)
+                                  : (cols + (uint64_t)(s - ncols) * col_stride + x1);
+      fe v = fe_load(src);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[8 * half_blk + k] = bswap32(v.v[7 - k]);
+    }
+    b2s_compress(h, m, 64u * (b + 1), b + 1 == nblk);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(nodes + 8 * (half + i));
+  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// Bottom level over raw byte leaves of any width (merkelize on bytes, merkle_tree.py:46-53).
+// Leaves are given in ORIGINAL order; np = 4*(n/4) leaves enter the tree.
+__global__ void __launch_bounds__(128) merkle_leaf_pairs_raw_kernel(const uint8_t* __restrict__ leaves, uint64_t np,
+                                                                     uint64_t leaf_len, uint64_t first,
+                                                                     uint64_t count, uint32_t* __restrict__ nodes) {
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint64_t i = first + t;  // node whose children are leaves: 2i >= np
+  const uint64_t q = np >> 2;
+  const uint64_t l0 = 2 * i - np;
+  const uint64_t x0 = (l0 & 3) * q + (l0 >> 2), x1 = ((l0 + 1) & 3) * q + ((l0 + 1) >> 2);
+  const uint64_t total = 2 * leaf_len;
+  uint32_t h[8];
+  b2s_init(h);
+  uint64_t off = 0;
+  do {
+    uint32_t m[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m[k] = 0;
+    uint64_t take = total - off < 64 ? total - off : 64;
+    for (uint64_t bi = 0; bi < take; ++bi) {
+      uint64_t pos = off + bi;
+      uint8_t byte = pos < leaf_len ? leaves[x0 * leaf_len + pos] : leaves[x1 * leaf_len + (pos - leaf_len)];
+      m[bi >> 2] |= (uint32_t)byte << (8 * (bi & 3));
+    }
+    off += take;
+    b2s_compress(h, m, (uint32_t)off, off == total);
+  } while (off < total);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) nodes[8 * i + k] = h[k];
+}
+
+// One heap level: node i = H(node 2i || node 2i+1) for i in [first, first+count).
+__global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict__ nodes, uint64_t first, uint64_t count) {
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint64_t i = first + t;
+  const uint4* src = reinterpret_cast<const uint4*>(nodes + 16 * i);
+  uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+  uint32_t m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+  uint32_t h[8];
+  b2s_init(h);
+  b2s_compress(h, m, 64u, true);
+  uint4* dst = reinterpret_cast<uint4*>(nodes + 8 * i);
+  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// All levels below `top` (a power of two <= 1024) in one CTA: nodes [1, top).
+__global__ void __launch_bounds__(512) merkle_top_kernel(uint32_t* __restrict__ nodes, uint32_t top, uint64_t np) {
+  for (uint32_t lo = top >> 1; lo >= 1; lo >>= 1) {
+    for (uint32_t i = lo + threadIdx.x; i < 2 * lo && i < np; i += blockDim.x) {
+      if (2ull * i >= np) continue;  // children are leaves: done by the leaf kernel
+      uint32_t m[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) m[k] = nodes[16 * i + k];
+      uint32_t h[8];
+      b2s_init(h);
+      b2s_compress(h, m, 64u, true);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nodes[8 * i + k] = h[k];
+    }
+    __syncthreads();
+  }
+}
+
+// Branches (mk_branch, merkle_tree.py:59-68) for column-leaf trees.  Output record per
+// query, as 32-bit words: own leaf (8*ncols) | sibling leaf (8*ncols) | sibling nodes up
+// to the root (8 words each).
+__global__ void __launch_bounds__(128) merkle_paths_cols_kernel(const fe* __restrict__ cols, uint64_t n, uint32_t ncols,
+                                                                 uint64_t col_stride, const uint32_t* __restrict__ nodes,
+                                                                 const uint64_t* __restrict__ idx, uint32_t* __restrict__ out,
+                                                                 uint64_t rec_words) {
+  const uint64_t qi = blockIdx.x;
+  const uint64_t x = idx[qi], ld4 = n >> 2;
+  const uint64_t perm = x / ld4 + 4 * (x % ld4);
+  const uint64_t index = perm + n;
+  uint32_t* o = out + qi * rec_words;
+  const uint32_t lw = 8 * ncols;
+  for (uint32_t w = threadIdx.x; w < 2 * lw; w += blockDim.x) {
+    uint32_t which = w / lw, ww = w % lw, c = ww >> 3, k = ww & 7;
+    uint64_t lp = which ? (perm ^ 1) : perm;
+    uint64_t row = (lp & 3) * ld4 + (lp >> 2);
+    o[w] = bswap32(cols[(uint64_t)c * col_stride + row].v[7 - k]);
+  }
+  uint32_t d = 1;
+  for (uint64_t id = index >> 1; id > 1; id >>= 1, ++d) {
+    if (threadIdx.x < 8) o[2 * lw + 8 * (d - 1) + threadIdx.x] = nodes[8 * (id ^ 1) + threadIdx.x];
+  }
+}
+
+// Power-of-two trees: nodes [1, np/2) have node children; levels go bottom-up, the last
+// (at most 1024-node) levels run inside one CTA.
+int reduce_levels(stk_ctx* c, uint32_t* nodes, uint64_t np) {
+  if (np < 4) return STK_OK;
+  uint64_t lo = np >> 2;
+  for (; lo >= 1024; lo >>= 1)
+    merkle_level_kernel<<<(unsigned)((lo + 255) / 256), 256, 0, c->stream>>>(nodes, lo, lo);
+  if (lo >= 1) merkle_top_kernel<<<1, 512, 0, c->stream>>>(nodes, (uint32_t)(2 * lo), np);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+}  // namespace
+
+#define STK_API extern "C" __attribute__((visibility("default")))
+
+STK_API int stk_merkle_commit(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                              uint8_t* d_nodes, uint8_t* h_root) {
+  if (!c || !d_cols || !d_nodes || ncols == 0) return STK_EINVAL;
+  const uint64_t np = 4 * (n / 4);
+  if (np == 0) return stk_fail(c, STK_EINVAL, "fewer than 4 leaves: the reference's permute4 yields an empty tree");
+  if (np & (np - 1)) {
+    // heap levels of a non power-of-two tree mix leaf parents and node parents; the column
+    // fast path keeps to the power-of-two sizes the prover produces
+    return stk_fail(c, STK_EUNSUPPORTED, "column commit needs a power-of-two row count (use stk_merkle_commit_raw)");
+  }
+  STK_CUDA(c, cudaMemsetAsync(d_nodes, 0, 32, c->stream));
+  const uint64_t half = np >> 1;
+  merkle_leaf_pairs_cols_kernel<<<(unsigned)((half + 255) / 256), 256, 0, c->stream>>>(
+      (const fe*)d_cols, np, (uint32_t)ncols, col_stride, (uint32_t*)d_nodes);
+  STK_CUDA(c, cudaGetLastError());
+  STK_TRY(reduce_levels(c, (uint32_t*)d_nodes, np));
+  if (h_root) {
+    STK_CUDA(c, cudaMemcpyAsync(h_root, d_nodes + 32, 32, cudaMemcpyDeviceToHost, c->stream));
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return STK_OK;
+}
+
+STK_API int stk_merkle_commit_raw(stk_ctx* c, const uint8_t* d_leaves, uint64_t n, uint64_t leaf_len, uint8_t* d_nodes,
+                                  uint8_t* h_root) {
+  if (!c || !d_leaves || !d_nodes || leaf_len == 0) return STK_EINVAL;
+  const uint64_t np = 4 * (n / 4);
+  if (np == 0) return stk_fail(c, STK_EINVAL, "fewer than 4 leaves: the reference's permute4 yields an empty tree");
+  STK_CUDA(c, cudaMemsetAsync(d_nodes, 0, 32, c->stream));
+  // nodes whose children are leaves: i in [np/2, np)
+  const uint64_t first = np >> 1, count = np - first;
+  merkle_leaf_pairs_raw_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(d_leaves, np, leaf_len, first,
+                                                                                       count, (uint32_t*)d_nodes);
+  STK_CUDA(c, cudaGetLastError());
+  // remaining nodes [1, np/2) by heap level, deepest first (any np, merkle_tree.py:54-55)
+  uint64_t lo = 1;
+  while (lo * 2 < first) lo *= 2;  // deepest level start: largest power of two < np/2 ... or == when pow2
+  if (first > 1) {
+    for (;; lo >>= 1) {
+      uint64_t hi = std::min<uint64_t>(2 * lo, first);
+      if (hi > lo) {
+        uint64_t cnt = hi - lo;
+        merkle_level_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>((uint32_t*)d_nodes, lo, cnt);
+      }
+      if (lo == 1) break;
+    }
+    STK_CUDA(c, cudaGetLastError());
+  }
+  if (h_root) {
+    STK_CUDA(c, cudaMemcpyAsync(h_root, d_nodes + 32, 32, cudaMemcpyDeviceToHost, c->stream));
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return STK_OK;
+}
+
+STK_API int stk_merkle_paths(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                             const uint8_t* d_nodes, const uint64_t* h_indices, uint64_t k, uint8_t* h_out,
+                             uint64_t rec_bytes) {
+  if (!c || !d_cols || !d_nodes || (!h_indices && k) || (!h_out && k)) return STK_EINVAL;
+  if (!k) return STK_OK;
+  const uint64_t np = 4 * (n / 4);
+  if (np == 0 || (np & (np - 1))) return stk_fail(c, STK_EUNSUPPORTED, "branch extraction needs a power-of-two tree");
+  uint32_t depth = 0;
+  while ((1ull << depth) < np) ++depth;
+  const uint64_t need = 2 * 32 * ncols + 32ull * (depth - 1);
+  if (rec_bytes < need || (rec_bytes & 3)) return stk_fail(c, STK_EINVAL, "record size %llu < %llu", (unsigned long long)rec_bytes, (unsigned long long)need);
+  for (uint64_t i = 0; i < k; ++i)
+    if (h_indices[i] >= np) return stk_fail(c, STK_EINDEX, "branch index out of range");
+  void* buf;
+  STK_TRY(stk_scratch(c, 2, k * 8 + k * rec_bytes, &buf));
+  uint64_t* d_idx = (uint64_t*)buf;
+  uint32_t* d_out = (uint32_t*)((char*)buf + k * 8);
+  STK_CUDA(c, cudaMemcpyAsync(d_idx, h_indices, k * 8, cudaMemcpyHostToDevice, c->stream));
+  merkle_paths_cols_kernel<<<(unsigned)k, 128, 0, c->stream>>>((const fe*)d_cols, np, (uint32_t)ncols, col_stride,
+                                                               (const uint32_t*)d_nodes, d_idx, d_out, rec_bytes / 4);
+  STK_CUDA(c, cudaGetLastError());
+  STK_CUDA(c, cudaMemcpyAsync(h_out, d_out, k * rec_bytes, cudaMemcpyDeviceToHost, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return STK_OK;
+}

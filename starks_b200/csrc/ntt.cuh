@@ -122,8 +122,8 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
   }
 }
 
-template <class F>
-__global__ void __launch_bounds__(512, 1) ntt_pass_kernel(const NttPass A, const F f) {
+template <class F, int MAXR>
+__global__ void __launch_bounds__(4096 >> MAXR, 1) ntt_pass_kernel(const NttPass A, const F f) {
   extern __shared__ uint32_t sm[];
   const uint32_t T = 1u << A.logT;
   const uint32_t xb = blockIdx.x;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(const NttPass A, const
     const int r = A.r[rd];
     a -= r;
     const bool first = rd == 0, last = rd == A.nrounds - 1;
-    if (r == 3) ntt_round<F, 3>(A, f, sm, T, Jcta, col0, a, first, last);
+    if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2)>(A, f, sm, T, Jcta, col0, a, first, last);
     else if (r == 2) ntt_round<F, 2>(A, f, sm, T, Jcta, col0, a, first, last);
     else ntt_round<F, 1>(A, f, sm, T, Jcta, col0, a, first, last);
     if (!last) __syncthreads();

@@ -189,16 +189,19 @@ int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
 
 static int ilog2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) ++l; return l; }
 
+static int ntt_max_radix() { return env_int("STK_NTT_RADIX", 3) >= 3 ? 3 : 2; }
+
 static void fill_rounds(NttPass& P) {
-  int k = P.k, rem = k % 3, idx = 0;
+  const int R = ntt_max_radix();
+  int k = P.k, rem = k % R, idx = 0;
   if (rem) P.r[idx++] = rem;
-  for (int i = 0; i < k / 3; ++i) P.r[idx++] = 3;
+  for (int i = 0; i < k / R; ++i) P.r[idx++] = R;
   P.nrounds = idx;
 }
 
 // Cuts the n index bits into passes (top bits first) and fixes each pass's tile geometry.
 static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
-  const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 12)));
+  const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 10)));
   const int kmax = std::min(logT, std::max(3, env_int("STK_NTT_KMAX", 11)));
   plan.clear();
   if (n <= kmax) {
@@ -240,23 +243,29 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
   return STK_OK;
 }
 
-template <class F>
-static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
+template <class F, int MAXR>
+static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
   static bool attr_done = false;
   if (!attr_done) {
-    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   const uint32_t T = 1u << P.logT;
-  unsigned threads = std::max(1u, T >> 3);
+  unsigned threads = std::max(1u, T >> MAXR);
   uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
   uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
   if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
   dim3 grid((unsigned)tiles, (unsigned)cols);
   size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
-  ntt_pass_kernel<F><<<grid, threads, smem, s>>>(P, f);
+  ntt_pass_kernel<F, MAXR><<<grid, threads, smem, s>>>(P, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
+}
+
+template <class F>
+static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
+  if (ntt_max_radix() >= 3) return launch_pass_r<F, 3>(c, s, P, f);
+  return launch_pass_r<F, 2>(c, s, P, f);
 }
 
 // direct DFT for orders that are not a power of two >= 8 (_simple_ft, starks/fft.py:287-300)

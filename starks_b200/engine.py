@@ -155,6 +155,51 @@ class Engine:
     do.free()
     return out
 
+  # ---- LDE / Merkle / FRI (device pointers) ------------------------------------
+  def lde(self, d_trace, steps, trace_stride, ext, cols, g2, d_evals, eval_stride, d_coeffs=0, coeff_stride=0):
+    self._check(self.lib.stk_lde(self.ctx, d_trace, steps, trace_stride, ext, cols,
+                                 _u32(int_to_limbs(int(g2) % self.p)), d_coeffs or None, coeff_stride, d_evals,
+                                 eval_stride))
+
+  def lde_commit(self, d_trace, steps, trace_stride, ext, cols, g2, d_evals, eval_stride, d_nodes):
+    root = (ctypes.c_uint8 * 32)()
+    self._check(self.lib.stk_lde_commit(self.ctx, d_trace, steps, trace_stride, ext, cols,
+                                        _u32(int_to_limbs(int(g2) % self.p)), d_evals, eval_stride, d_nodes, root))
+    return bytes(root)
+
+  def merkle_commit(self, d_cols, n, ncols, col_stride, d_nodes, want_root=True):
+    root = (ctypes.c_uint8 * 32)()
+    self._check(self.lib.stk_merkle_commit(self.ctx, d_cols, n, ncols, col_stride, d_nodes,
+                                           root if want_root else None))
+    return bytes(root) if want_root else None
+
+  def merkle_commit_raw(self, d_leaves, n, leaf_len, d_nodes):
+    root = (ctypes.c_uint8 * 32)()
+    self._check(self.lib.stk_merkle_commit_raw(self.ctx, d_leaves, n, leaf_len, d_nodes, root))
+    return bytes(root)
+
+  def merkle_paths(self, d_cols, n, ncols, col_stride, d_nodes, indices):
+    """mk_branch for many indices at once -> list of branches (lists of bytes)."""
+    k = len(indices)
+    if k == 0:
+      return []
+    depth = (4 * (n // 4)).bit_length() - 1
+    L = 32 * ncols
+    rec = 2 * L + 32 * (depth - 1)
+    idx = np.asarray(indices, dtype=np.uint64)
+    out = np.empty((k, rec), dtype=np.uint8)
+    self._check(self.lib.stk_merkle_paths(self.ctx, d_cols, n, ncols, col_stride, d_nodes, idx.ctypes.data, k,
+                                          out.ctypes.data, rec))
+    res = []
+    for r in out:
+      b = r.tobytes()
+      res.append([b[:L], b[L:2 * L]] + [b[2 * L + 32 * j:2 * L + 32 * (j + 1)] for j in range(depth - 1)])
+    return res
+
+  def fri_fold4(self, d_vals, n, root, special_x, d_out):
+    self._check(self.lib.stk_fri_fold4(self.ctx, d_vals, n, _u32(int_to_limbs(int(root) % self.p)),
+                                       _u32(int_to_limbs(int(special_x))), d_out))
+
   def microbench(self, which, iters):
     ms, ops = ctypes.c_float(), ctypes.c_double()
     self._check(self.lib.stk_microbench(self.ctx, which, iters, ctypes.byref(ms), ctypes.byref(ops)))
