@@ -126,6 +126,30 @@ int stk_merkle_paths(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t 
 int stk_fri_fold4(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, const uint32_t root[8],
                   const uint32_t special_x[8], uint32_t* d_out);
 
+/* ---- prover constructions between the commitments (starks/stark.py:38-177) ---------- */
+/* construct_constraint_polynomials in evaluation form (stark.py:38-55):
+ * cev[j][i] = pev[j][(i+ext) mod n] - step_j(pev[0][i], ..., pev[width-1][i]).  The step
+ * polynomials arrive as a monomial list (the reference's MultiVarPoly is a dict
+ * monomial -> coefficient, starks/multivariate_polynomial.py): monomial m contributes
+ * coeffs[m] * prod_k X_{k+1}^exps[width*m+k] to constraint out[m].  width <= 12. */
+int stk_constraint_eval(stk_ctx* ctx, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                        uint64_t col_stride, const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs,
+                        const uint8_t* h_mono_exps, uint64_t nmono, uint32_t* d_cev, uint64_t out_stride);
+/* construct_remainder_polynomials (stark.py:57-78) on coefficient vectors of length n:
+ * D = C / Z with Z = (X^steps - 1)/(X - last), computed as C*(X-last) / (X^steps - 1).
+ * *h_bad = number of non-zero remainder coefficients (the reference asserts divisibility). */
+int stk_quotient_z(stk_ctx* ctx, const uint32_t* d_ccoef, uint64_t n, uint64_t steps, const uint32_t last[8],
+                   uint32_t* d_dcoef, uint32_t* h_bad);
+/* Quotient of a polynomial (n coefficients, low -> high) by (X - r), as Polynomial.__divmod__
+ * (starks/polynomial.py:128-143) yields it: out[k] = sum_{i>k} a[i] r^(i-k-1), k < n-1.
+ * r = 1, or r of multiplicative order r_order >= n (its power tables are cached). */
+int stk_div_linear(stk_ctx* ctx, const uint32_t* d_a, uint64_t n, const uint32_t r[8], uint64_t r_order,
+                   uint32_t* d_out);
+/* compute_pseudorandom_linear_combination (stark.py:130-177) in evaluation form:
+ * out[i] = sum_c weights[c] * cols[c][i]. */
+int stk_lincomb(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                const uint32_t* h_weights, uint32_t* d_out);
+
 /* ---- K0: integer-pipe microbenchmarks (roofline denominators) ---------------------- */
 /* which: 0 IMAD, 1 IMAD.WIDE, 2 IADD3, 3 IMAD.HI, 4 IADD3+LOP3+SHF (BLAKE2s mix),
  * 5 field multiply, 6 NTT butterfly, 7 IMAD+IADD3, 8 IMAD.WIDE+IADD3, 9 carry-chain adds,

@@ -52,6 +52,10 @@ SIGNATURES = {
     "stk_merkle_commit_raw": (cint, [vp, vp, u64, u64, vp, vp]),
     "stk_merkle_paths": (cint, [vp, vp, u64, u64, u64, vp, vp, u64, vp, u64]),
     "stk_fri_fold4": (cint, [vp, vp, u64, u32p, u32p, vp]),
+    "stk_constraint_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, vp, u64]),
+    "stk_quotient_z": (cint, [vp, vp, u64, u64, u32p, vp, ctypes.POINTER(ctypes.c_uint32)]),
+    "stk_div_linear": (cint, [vp, vp, u64, u32p, u64, vp]),
+    "stk_lincomb": (cint, [vp, vp, u64, u64, u64, vp, vp]),
     "stk_microbench": (cint, [vp, cint, u64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -81,15 +81,15 @@ __device__ __forceinline__ void mul_row_first(uint32_t* acc, const uint32_t* a, 
 #pragma unroll
   for (int j = 0; j < 8; j += 2)
     asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;"
-        : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+        : "=&r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(b));  // %0 is written before %2 is last read
 }
 __device__ __forceinline__ void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
   asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
-      : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
+      : "+&r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
 #pragma unroll
   for (int j = 2; j < 8; j += 2)
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
-        : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+        : "+&r"(acc[j]), "+r"(acc[j + 1]) : "r"(a[j]), "r"(b));
   asm volatile("addc.u32 %0, 0, 0;" : "=r"(acc[8]));
 }
 __device__ __forceinline__ void mul512(uint32_t* T, const uint32_t* a, const uint32_t* b) {

@@ -1,0 +1,291 @@
+// stark.cu -- the prover's polynomial constructions between the commitments, in
+// O(n log n) evaluation/NTT form.  The reference builds them in coefficient form with
+// O(n^2) Horner composition and schoolbook long division (starks/stark.py:38-104,
+// starks/polynomial.py:128-143); arithmetic is exact mod p, so the polynomials -- and hence
+// every committed evaluation -- are identical.
+//
+//   constraint evaluations   C_j(x_i) = P_j(G1*x_i) - step_j(P_1(x_i), ..., P_w(x_i))
+//                            with P_j(G1*x_i) = Pev_j[(i+ext) mod N]        (stark.py:38-55)
+//   quotient by Z            D_j = C_j*(X-last) / (X^steps - 1)             (stark.py:57-78)
+//   division by X - r        quotient coefficients as geometric suffix sums (stark.py:80-104,
+//                            B_j = (P_j - I_j) / ((X-1)(X-last)))
+//   linear combination       l = sum_c weight_c * column_c                  (stark.py:130-177)
+#include <vector>
+#include "ctx.h"
+
+using namespace stk;
+
+namespace {
+
+struct Monomial {
+  fe coeff_tw;       // coefficient in twiddle form
+  uint32_t out;      // which constraint it belongs to
+  uint8_t exp[12];   // exponent of each state variable (width <= 12)
+};
+
+// One thread per evaluation point.  State values P_k(x_i) are loaded once; every monomial is
+// coeff * prod_k P_k^e_k by repeated multiplication (degrees are tiny: <= extension factor).
+template <class F>
+__global__ void __launch_bounds__(128) constraint_eval_kernel(const fe* __restrict__ pev, uint64_t n, uint64_t ext,
+                                                              uint32_t width, uint64_t col_stride,
+                                                              const Monomial* __restrict__ monos, uint32_t nmono,
+                                                              fe* __restrict__ cev, uint64_t out_stride, const F f) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe st[12], st_tw[12];
+  for (uint32_t k = 0; k < width; ++k) {
+    st[k] = fe_load(pev + k * col_stride + i);
+    st_tw[k] = f.to_tw(st[k]);
+  }
+  const uint64_t inext = (i + ext) % n;
+  for (uint32_t j = 0; j < width; ++j) {
+    fe acc = fe_zero();
+    for (uint32_t m = 0; m < nmono; ++m) {
+      if (monos[m].out != j) continue;
+      fe term = f.from_tw(monos[m].coeff_tw);  // plain coefficient
+      for (uint32_t k = 0; k < width; ++k)
+        for (uint32_t e = 0; e < monos[m].exp[k]; ++e) term = f.mul_tw(term, st_tw[k]);
+      acc = f.add(acc, term);
+    }
+    fe nxt = fe_load(pev + j * col_stride + inext);
+    fe_store(cev + j * out_stride + i, f.sub(nxt, acc));
+  }
+}
+
+// E = C*(X - last) has coefficients e[i] = c[i-1] - last*c[i] (c[-1] = c[n] = 0, i <= n).
+template <class F>
+__device__ __forceinline__ fe e_coeff(const fe* c, uint64_t n, uint64_t i, const fe& last_tw, const F& f) {
+  fe lo = (i >= 1 && i - 1 < n) ? fe_load(c + i - 1) : fe_zero();
+  fe hi = (i < n) ? f.mul_tw(fe_load(c + i), last_tw) : fe_zero();
+  return f.sub(lo, hi);
+}
+
+// D = E / (X^steps - 1): d[i] = e[i+steps] + d[i+steps], high to low; one thread per
+// residue r = i mod steps walks its chain (length n/steps).  Remainder e[r] + d[r] must be 0
+// (the reference asserts `cp % z == 0`, stark.py:74-75): violations are counted.
+template <class F>
+__global__ void __launch_bounds__(256) quotient_z_kernel(const fe* __restrict__ c, uint64_t n, uint64_t steps,
+                                                         fe last_tw, fe* __restrict__ d, uint32_t* __restrict__ bad,
+                                                         const F f) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= steps) return;
+  const uint64_t chain = n / steps;  // e has n+1 coefficients: indices r + m*steps, m <= chain (only r = 0 reaches n)
+  fe acc = fe_zero();                // d[r + m*steps] for the m above
+  // top: indices i = r + m*steps with i + steps > n have d[i] = 0
+  for (uint64_t m = chain; m-- > 0;) {
+    const uint64_t i = r + m * steps;  // computing d[i] = e[i+steps] + d[i+steps]
+    fe e = (i + steps <= n) ? e_coeff(c, n, i + steps, last_tw, f) : fe_zero();
+    acc = f.add(e, acc);
+    fe_store(d + i, acc);
+  }
+  fe rem = f.add(e_coeff(c, n, r, last_tw, f), acc);
+  if (!fe_is_zero(rem)) atomicAdd(bad, 1u);
+}
+
+// ---- geometric suffix sums: out[k] = sum_{i>k} a[i] * r^(i-k-1),  k < n-1 ------------------
+// With a'[i] = a[i]*r^i this is r^-(k+1) * S[k], S the exclusive suffix sum of a'.
+constexpr int kScanChunk = 8;      // elements per thread
+constexpr int kScanThreads = 256;  // threads per block -> 2048 elements per block
+
+template <class F>
+__device__ __forceinline__ fe scan_load(const fe* a, const fe* rpow, uint64_t n, uint64_t i, const F& f) {
+  if (i >= n) return fe_zero();
+  fe v = fe_load(a + i);
+  return rpow ? f.mul_tw(v, fe_load_ro(rpow + i)) : v;
+}
+
+// phase 1: block totals
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_block_totals_kernel(const fe* __restrict__ a, const fe* __restrict__ rpow,
+                                                                         uint64_t n, fe* __restrict__ totals, const F f) {
+  __shared__ fe sh[kScanThreads];
+  const uint64_t base = ((uint64_t)blockIdx.x * kScanThreads + threadIdx.x) * kScanChunk;
+  fe s = fe_zero();
+#pragma unroll
+  for (int u = 0; u < kScanChunk; ++u) s = f.add(s, scan_load(a, rpow, n, base + u, f));
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = kScanThreads / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] = f.add(sh[threadIdx.x], sh[threadIdx.x + off]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = sh[0];
+}
+
+// phase 2: exclusive suffix scan of the block totals (single block, sequential over <= 64K entries)
+template <class F>
+__global__ void scan_totals_kernel(fe* totals, uint64_t nblocks, const F f) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  fe run = fe_zero();
+  for (uint64_t b = nblocks; b-- > 0;) {
+    fe t = totals[b];
+    totals[b] = run;  // sum of all blocks after b
+    run = f.add(run, t);
+  }
+}
+
+// phase 3: exclusive suffix sums inside each block + block offset, then unscale
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_finish_kernel(const fe* __restrict__ a, const fe* __restrict__ rpow,
+                                                                   const fe* __restrict__ rinvpow, uint64_t n,
+                                                                   const fe* __restrict__ totals, fe* __restrict__ out,
+                                                                   const F f) {
+  __shared__ fe sh[kScanThreads];
+  const uint64_t base = ((uint64_t)blockIdx.x * kScanThreads + threadIdx.x) * kScanChunk;
+  fe v[kScanChunk];
+  fe s = fe_zero();
+#pragma unroll
+  for (int u = 0; u < kScanChunk; ++u) { v[u] = scan_load(a, rpow, n, base + u, f); s = f.add(s, v[u]); }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  // inclusive suffix scan over thread sums (Hillis-Steele)
+  for (int off = 1; off < kScanThreads; off <<= 1) {
+    fe t = fe_zero();
+    bool has = threadIdx.x + off < kScanThreads;
+    if (has) t = sh[threadIdx.x + off];
+    __syncthreads();
+    if (has) sh[threadIdx.x] = f.add(sh[threadIdx.x], t);
+    __syncthreads();
+  }
+  // sum of everything after this thread's chunk
+  fe after = (threadIdx.x + 1 < kScanThreads) ? sh[threadIdx.x + 1] : fe_zero();
+  after = f.add(after, totals[blockIdx.x]);
+  // walk the chunk from its top: S[k] = sum_{i>k} a'[i]
+#pragma unroll
+  for (int u = kScanChunk - 1; u >= 0; --u) {
+    const uint64_t k = base + u;
+    if (k + 1 < n) {
+      fe r = after;
+      if (rinvpow) r = f.mul_tw(r, fe_load_ro(rinvpow + ((k + 1) % n)));  // r^-(k+1)
+      fe_store(out + k, r);
+    }
+    after = f.add(after, v[u]);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) lincomb_kernel(const fe* __restrict__ cols, uint64_t n, uint32_t ncols,
+                                                      uint64_t col_stride, const fe* __restrict__ weights_tw,
+                                                      fe* __restrict__ out, const F f) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe acc = fe_zero();
+  for (uint32_t c = 0; c < ncols; ++c)
+    acc = f.add(acc, f.mul_tw(fe_load(cols + c * col_stride + i), fe_load_ro(weights_tw + c)));
+  fe_store(out + i, acc);
+}
+
+template <class F>
+int div_linear_impl(stk_ctx* c, const fe* a, uint64_t n, const fe* rpow, const fe* rinvpow, fe* out, const F& f) {
+  const uint64_t per_block = (uint64_t)kScanChunk * kScanThreads;
+  const uint64_t nblocks = (n + per_block - 1) / per_block;
+  void* t;
+  STK_TRY(stk_scratch(c, 2, nblocks * sizeof(fe), &t));
+  fe* totals = (fe*)t;
+  scan_block_totals_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, n, totals, f);
+  scan_totals_kernel<F><<<1, 32, 0, c->stream>>>(totals, nblocks, f);
+  scan_finish_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rinvpow, n, totals, out, f);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+}  // namespace
+
+#define STK_API extern "C" __attribute__((visibility("default")))
+
+// step polynomials as a monomial list: for monomial m, out[m] = constraint index,
+// coeffs[8*m..] = coefficient limbs (canonical), exps[width*m + k] = exponent of X_{k+1}.
+STK_API int stk_constraint_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                                uint64_t col_stride, const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs,
+                                const uint8_t* h_mono_exps, uint64_t nmono, uint32_t* d_cev, uint64_t out_stride) {
+  if (!c || !d_pev || !d_cev || (!nmono ? false : (!h_mono_out || !h_mono_coeffs || !h_mono_exps))) return STK_EINVAL;
+  if (width == 0 || width > 12) return stk_fail(c, STK_EUNSUPPORTED, "state width must be in 1..12");
+  std::vector<Monomial> ms(nmono ? nmono : 1);
+  for (uint64_t m = 0; m < nmono; ++m) {
+    if (h_mono_out[m] >= width) return stk_fail(c, STK_EINVAL, "monomial output index out of range");
+    fe cf = host::reduce(stk_load_fe(h_mono_coeffs + 8 * m), c->p);
+    ms[m].coeff_tw = stk_h_to_tw(c, cf);
+    ms[m].out = h_mono_out[m];
+    for (uint64_t k = 0; k < 12; ++k) ms[m].exp[k] = k < width ? h_mono_exps[width * m + k] : 0;
+  }
+  void* t;
+  STK_TRY(stk_scratch(c, 2, ms.size() * sizeof(Monomial), &t));
+  STK_CUDA(c, cudaMemcpyAsync(t, ms.data(), ms.size() * sizeof(Monomial), cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));  // ms is a stack-owned staging buffer
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (c->is_stark)
+    constraint_eval_kernel<StarkField><<<blocks, 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
+                                                                      (const Monomial*)t, (uint32_t)nmono, (fe*)d_cev,
+                                                                      out_stride, StarkField());
+  else
+    constraint_eval_kernel<MontField><<<blocks, 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
+                                                                     (const Monomial*)t, (uint32_t)nmono, (fe*)d_cev,
+                                                                     out_stride, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+// D = C * (X - last) / (X^steps - 1) on coefficient vectors of length n (n a multiple of
+// steps).  *h_bad receives the number of non-zero remainder coefficients (0 = exact).
+STK_API int stk_quotient_z(stk_ctx* c, const uint32_t* d_ccoef, uint64_t n, uint64_t steps, const uint32_t last[8],
+                           uint32_t* d_dcoef, uint32_t* h_bad) {
+  if (!c || !d_ccoef || !d_dcoef || !last || steps == 0 || n % steps) return STK_EINVAL;
+  void* t;
+  STK_TRY(stk_scratch(c, 2, 64, &t));
+  STK_CUDA(c, cudaMemsetAsync(t, 0, 4, c->stream));
+  fe last_tw = stk_h_to_tw(c, host::reduce(stk_load_fe(last), c->p));
+  unsigned blocks = (unsigned)((steps + 255) / 256);
+  if (c->is_stark)
+    quotient_z_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_ccoef, n, steps, last_tw, (fe*)d_dcoef,
+                                                                 (uint32_t*)t, StarkField());
+  else
+    quotient_z_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_ccoef, n, steps, last_tw, (fe*)d_dcoef,
+                                                                (uint32_t*)t, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  if (h_bad) {
+    STK_CUDA(c, cudaMemcpyAsync(h_bad, t, 4, cudaMemcpyDeviceToHost, c->stream));
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return STK_OK;
+}
+
+// Quotient of a (n coefficients, low -> high) by (X - r): out[k] = sum_{i>k} a[i] r^(i-k-1),
+// k < n-1 (out[n-1] is not written).  r must be 1 or an element whose order divides n... the
+// powers r^i and r^-i (i < n) are taken from the cached tables of r and r^-1.
+STK_API int stk_div_linear(stk_ctx* c, const uint32_t* d_a, uint64_t n, const uint32_t r[8], uint64_t r_order,
+                           uint32_t* d_out) {
+  if (!c || !d_a || !d_out || !r || n < 2) return STK_EINVAL;
+  fe rr = host::reduce(stk_load_fe(r), c->p);
+  fe one = host::reduce(host::from_u64(1), c->p);
+  const fe* rpow = nullptr;
+  const fe* rinvpow = nullptr;
+  if (!fe_eq(rr, one)) {
+    if (r_order < n) return stk_fail(c, STK_EINVAL, "order of r must be at least the coefficient count");
+    if (!fe_eq(stk_h_pow(c, rr, r_order), one)) return stk_fail(c, STK_EINVAL, "r^order != 1");
+    STK_TRY(stk_get_table(c, rr, r_order, &rpow));
+    STK_TRY(stk_get_table(c, stk_h_inv(c, rr), r_order, &rinvpow));
+  }
+  if (c->is_stark) return div_linear_impl<StarkField>(c, (const fe*)d_a, n, rpow, rinvpow, (fe*)d_out, StarkField());
+  return div_linear_impl<MontField>(c, (const fe*)d_a, n, rpow, rinvpow, (fe*)d_out, c->mont);
+}
+
+// out[i] = sum_c weights[c] * cols[c][i]
+STK_API int stk_lincomb(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                        const uint32_t* h_weights, uint32_t* d_out) {
+  if (!c || !d_cols || !d_out || !h_weights || ncols == 0) return STK_EINVAL;
+  std::vector<fe> w(ncols);
+  for (uint64_t i = 0; i < ncols; ++i) w[i] = stk_h_to_tw(c, host::reduce(stk_load_fe(h_weights + 8 * i), c->p));
+  void* t;
+  STK_TRY(stk_scratch(c, 2, ncols * sizeof(fe), &t));
+  STK_CUDA(c, cudaMemcpyAsync(t, w.data(), ncols * sizeof(fe), cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (c->is_stark)
+    lincomb_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_cols, n, (uint32_t)ncols, col_stride,
+                                                              (const fe*)t, (fe*)d_out, StarkField());
+  else
+    lincomb_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_cols, n, (uint32_t)ncols, col_stride,
+                                                             (const fe*)t, (fe*)d_out, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}

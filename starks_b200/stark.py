@@ -1,0 +1,232 @@
+"""Drop-in for the prover/verifier driver of starks/stark.py: STARK(field, steps,
+extension_factor, width, step_polys).mk_proof(witness, boundary) / .verify_proof(proof,
+witness, boundary), get_pseudorandom_ks and the construct_* helpers' results.
+
+mk_proof keeps every column on the device from the witness upload to the last FRI layer:
+LDE (stk_lde), constraint evaluations (stk_constraint_eval), quotients (stk_quotient_z,
+stk_div_linear), Merkle commitments (stk_merkle_commit), linear combination (stk_lincomb),
+branch gathers (stk_merkle_paths) and FRI folds (stk_fri_fold4).  Only 32-byte roots, the
+Fiat-Shamir scalars and the opened branches cross to the host.  The proof object
+[m_root, l_root, branches, fri_proof] (stark.py:270-277) is bit-identical to the reference's.
+verify_proof is host-side glue (80 positions + FRI checks) mirroring stark.py:281-372."""
+import time
+from hashlib import blake2s
+
+import numpy as np
+
+from .engine import default_engine
+from .fri import FRI, DeviceLayer
+from .limbs import int_to_limbs, ints_to_limbs, limbs_to_ints
+from .merkle_tree import unpack_merkle_leaf, verify_branch
+from .modp import element_to_int
+from .polynomial import monomials_of
+from .utils import get_pseudorandom_indices
+
+blake = lambda x: blake2s(x).digest()
+
+
+def get_pseudorandom_ks(m_root: bytes, num: int):
+  """starks/stark.py:106-126 (the salts are the ASCII strings b'0x01'...)."""
+  if 0 <= num and num <= 4:
+    byte_list = [b"0x01", b"0x02", b"0x03", b"0x04"]
+    return [int.from_bytes(blake(m_root + byte_list[ind]), "big") for ind in range(num)]
+  elif num < 10:
+    byte_list = [("0x0%s" % str(i)).encode("UTF-8") for i in range(num)]
+    return [int.from_bytes(blake(m_root + byte_list[ind]), "big") for ind in range(num)]
+
+
+def _interp2(p, x0, x1, y0, y1):
+  """lagrange_interp_2 (starks/poly_utils.py:397-410) -> coefficients [i0, i1]."""
+  eq0, eq1 = [(-x1) % p, 1], [(-x0) % p, 1]
+  e0, e1 = (eq0[0] + x0) % p, (eq1[0] + x1) % p
+  invall = pow(e0 * e1 % p, -1, p)
+  inv_y0 = y0 * invall % p * e1 % p
+  inv_y1 = y1 * invall % p * e0 % p
+  return [(eq0[i] * inv_y0 + eq1[i] * inv_y1) % p for i in range(2)]
+
+
+class STARK(object):
+  """Generates and verifies STARKs (starks/stark.py:179-402)."""
+
+  def __init__(self, field, steps, extension_factor, width, step_polys, spot_check_security_factor=80,
+               engine=None):
+    self.field = field
+    self.width = width
+    self.steps = steps
+    self.step_polys = step_polys
+    self.extension_factor = extension_factor
+    self.precision = steps * extension_factor
+    self.spot_check_security_factor = spot_check_security_factor
+    self._engine = engine
+    p = self.field.p
+    self.G2 = field(7)**((p - 1) // self.precision)                      # :217
+    self.G1 = self.G2**extension_factor                                  # :220
+    self.last_step_position = self.G2**((steps - 1) * extension_factor)  # xs[(steps-1)*ext], :223-224
+    self._monomials = [monomials_of(sp, width, p) for sp in step_polys]
+    self.timings = {}
+
+  @property
+  def xs(self):
+    from .utils import get_power_cycle
+    return get_power_cycle(self.G2, self.field, engine=self._engine)
+
+  def get_degree(self):
+    return max(max([sum(k) for k, _ in m] or [0]) for m in self._monomials)  # :230-231
+
+  # ----------------------------------------------------------------- prover
+  def _witness_limbs(self, witness):
+    p = self.field.p
+    if isinstance(witness, np.ndarray):
+      assert witness.shape == (self.width, self.steps, 8)
+      return np.ascontiguousarray(witness, dtype=np.uint32)
+    assert len(witness) == self.width
+    return np.stack([ints_to_limbs([element_to_int(v) % p for v in col]) for col in witness])
+
+  def mk_proof(self, witness, boundary, keep_device=False):
+    """stark.py:233-279."""
+    t_start = time.time()
+    eng = self._engine or default_engine()
+    p = self.field.p
+    eng.set_field(p)
+    w, steps, ext, N = self.width, self.steps, self.extension_factor, self.precision
+    G2, last = int(self.G2), int(self.last_step_position)
+    tr = self._witness_limbs(witness)
+    assert tr.shape[1] == steps
+    E = 32
+    d_trace = eng.alloc(w * steps * E).upload(tr)
+    d_pcoef = eng.alloc(w * steps * E)
+    d_cols = eng.alloc(3 * w * N * E)        # rows: P_1..P_w, D_1..D_w, B_1..B_w (stark.py:247)
+    d_t1 = eng.alloc(w * N * E)
+    d_t2 = eng.alloc(w * N * E)
+    # construct_trace_polynomials (:27-36) + evaluation (:254-256)
+    eng.lde(d_trace.ptr, steps, steps, ext, w, G2, d_cols.ptr, N, d_coeffs=d_pcoef.ptr, coeff_stride=steps)
+    # construct_constraint_polynomials (:38-55), evaluation form
+    mono_out, mono_coef, mono_exp = [], [], []
+    for j, ms in enumerate(self._monomials):
+      for exps, c in ms:
+        mono_out.append(j)
+        mono_coef.append(c)
+        mono_exp.append(list(exps))
+    nm = len(mono_out)
+    h_out = np.asarray(mono_out, dtype=np.uint32)
+    h_coef = ints_to_limbs(mono_coef) if nm else np.zeros((0, 8), np.uint32)
+    h_exp = np.asarray(mono_exp, dtype=np.uint8).reshape(nm, w) if nm else np.zeros((0, w), np.uint8)
+    eng._check(eng.lib.stk_constraint_eval(eng.ctx, d_cols.ptr, N, ext, w, N, h_out.ctypes.data, h_coef.ctypes.data,
+                                           h_exp.ctypes.data, nm, d_t1.ptr, N))
+    # construct_remainder_polynomials (:57-78): D = C / Z in coefficient form
+    eng.ntt(d_t1.ptr, N, N, d_t2.ptr, N, N, w, G2, inverse=True)
+    import ctypes
+    bad = ctypes.c_uint32(0)
+    last_l = int_to_limbs(last)
+    for j in range(w):
+      eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * N * E), N, steps, last_l.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                        d_t1.at(j * N * E), ctypes.byref(bad)))
+      assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
+    eng.ntt(d_t1.ptr, N, N, d_cols.at(w * N * E), N, N, w, G2)
+    # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
+    out_vals = limbs_to_ints(tr[:, -1, :])
+    one_l = int_to_limbs(1)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    for j in range(w):
+      (_, _, input_value) = boundary[j]
+      interp = _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
+      d_i = eng.alloc(2 * E).upload(ints_to_limbs(interp))
+      a = d_t2.at(j * steps * E)
+      eng._check(eng.lib.stk_memcpy_d2d(eng.ctx, a, d_pcoef.at(j * steps * E), steps * E))
+      eng._check(eng.lib.stk_vec_op(eng.ctx, 1, a, d_i.ptr, a, 2))
+      q1 = d_t1.at(j * steps * E)
+      eng._check(eng.lib.stk_div_linear(eng.ctx, a, steps, one_l.ctypes.data_as(u32p), 1, q1))
+      eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
+      eng.sync()
+      d_i.free()
+    eng.ntt(d_t2.ptr, steps - 2, steps, d_cols.at(2 * w * N * E), N, N, w, G2)
+    # merkelize_polynomial_evaluations (:257)
+    d_mnodes = eng.alloc(32 * N)
+    m_root = eng.merkle_commit(d_cols.ptr, N, 3 * w, N, d_mnodes.ptr)
+    # compute_pseudorandom_linear_combination (:130-177), evaluation form
+    k1, k2, k3, k4 = get_pseudorandom_ks(m_root, 4)
+    l_ks = get_pseudorandom_ks(m_root, w)
+    c = pow(pow(G2, steps, p), N - 1, p)     # powers[i] with the leaked i = precision-1 (:153-160)
+    wP, wD, wB = [], [], []
+    for j in range(w):
+      aj = (1 + l_ks[j] * c) % p
+      wD.append(aj)
+      wP.append(aj * ((k1 + k2 * c) % p) % p)
+      wB.append(aj * ((k3 + k4 * c) % p) % p)
+    weights = ints_to_limbs(wP + wD + wB)
+    d_l = eng.alloc(N * E)
+    eng._check(eng.lib.stk_lincomb(eng.ctx, d_cols.ptr, N, 3 * w, N, weights.ctypes.data, d_l.ptr))
+    d_lnodes = eng.alloc(32 * N)
+    l_root = eng.merkle_commit(d_l.ptr, N, 1, N, d_lnodes.ptr)           # :262-263
+    # compute_merkle_spot_checks (:390-402), samples = 80
+    positions = get_pseudorandom_indices(l_root, N, 80, exclude_multiples_of=ext)
+    mb = eng.merkle_paths(d_cols.ptr, N, 3 * w, N, d_mnodes.ptr,
+                          [x for pos in positions for x in (pos, (pos + ext) % N)])
+    lb = eng.merkle_paths(d_l.ptr, N, 1, N, d_lnodes.ptr, positions)
+    branches = []
+    for i in range(len(positions)):
+      branches += [mb[2 * i], mb[2 * i + 1], lb[i]]
+    # FRI on l (:267-276); its first layer's tree is l_mtree
+    fri = FRI(self.field, engine=eng)
+    fri_proof = fri.prove_from_device(DeviceLayer(eng, d_l.ptr, N, d_lnodes.ptr, l_root), G2,
+                                      steps * self.get_degree(), exclude_multiples_of=ext)
+    proof = [m_root, l_root, branches, fri_proof]
+    self.timings["mk_proof_s"] = time.time() - t_start
+    if keep_device:
+      self.device = dict(cols=d_cols, pcoef=d_pcoef, l=d_l, mnodes=d_mnodes, lnodes=d_lnodes)
+    else:
+      for b in (d_trace, d_pcoef, d_cols, d_t1, d_t2, d_mnodes, d_l, d_lnodes):
+        b.free()
+    return proof
+
+  # --------------------------------------------------------------- verifier
+  def verify_proof(self, proof, witness, boundary):
+    """stark.py:281-317 (host-side; the reference hands the verifier the witness, :370)."""
+    m_root, l_root, branches, fri_proof = proof
+    fri = FRI(self.field, engine=self._engine)
+    assert fri.verify_proximity_proof(fri_proof, l_root, self.G2, self.steps * self.get_degree(),
+                                      exclude_multiples_of=self.extension_factor)
+    samples = self.spot_check_security_factor
+    positions = get_pseudorandom_indices(l_root, self.precision, samples,
+                                         exclude_multiples_of=self.extension_factor)
+    ks = get_pseudorandom_ks(m_root, 4)
+    for i, pos in enumerate(positions):
+      self.verify_proof_at_position(witness, boundary, ks, proof, i, pos)
+    return True
+
+  def _step(self, j, state, p):
+    acc = 0
+    for exps, c in self._monomials[j]:
+      t = c
+      for k, e in enumerate(exps):
+        t = t * pow(state[k], e, p) % p
+      acc = (acc + t) % p
+    return acc
+
+  def verify_proof_at_position(self, witness, boundary, ks, proof, i, pos):
+    """stark.py:319-372."""
+    p, width = self.field.p, self.width
+    m_root, l_root, branches, fri_proof = proof
+    G2, last = int(self.G2), int(self.last_step_position)
+    x = pow(G2, pos, p)
+    leaf1 = unpack_merkle_leaf(verify_branch(m_root, pos, branches[i * 3]), width, 3)
+    leaf2 = unpack_merkle_leaf(verify_branch(m_root, (pos + self.extension_factor) % self.precision,
+                                             branches[i * 3 + 1]), width, 3)
+    verify_branch(l_root, pos, branches[i * 3 + 2], output_as_int=True)
+    f_ = lambda b: int.from_bytes(b, "big")   # field(bytes) does not reduce; values are canonical
+    p_of_x = [f_(v) for v in leaf1[:width]]
+    p_of_g1x = [f_(v) for v in leaf2[:width]]
+    d_of_x = [f_(v) for v in leaf1[width:2 * width]]
+    b_of_x = [f_(v) for v in leaf1[2 * width:]]
+    zvalue = (pow(x, self.steps, p) - 1) * pow((x - last) % p, -1, p) % p
+    for dim in range(width):                                             # transition constraints
+      assert (p_of_g1x[dim] - self._step(dim, p_of_x, p) - zvalue * d_of_x[dim]) % p == 0
+    zeropoly2_x = (x - 1) * (x - last) % p
+    for dim in range(width):                                             # boundary constraints
+      (_, _, input_value) = boundary[dim]
+      if isinstance(witness, np.ndarray):
+        output_dim = limbs_to_ints(witness[dim, -1:, :])[0]
+      else:
+        output_dim = element_to_int(witness[dim][-1]) % p
+      i0, i1 = _interp2(p, 1, last, element_to_int(input_value) % p, output_dim)
+      assert (p_of_x[dim] - b_of_x[dim] * zeropoly2_x - (i0 + i1 * x)) % p == 0
