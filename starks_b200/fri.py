@@ -12,7 +12,7 @@ import numpy as np
 
 from .engine import default_engine
 from .limbs import ints_to_limbs, limbs_to_be_bytes, limbs_to_ints
-from .merkle_tree import merkelize, verify_branch
+from .merkle_tree import verify_branch
 from .modp import element_to_int
 from .utils import get_pseudorandom_indices, multiplicative_order
 
@@ -115,8 +115,7 @@ class SmoothSubgroupFRI(object):
       roudeg //= 4
     data = [int.from_bytes(x, "big") for x in proof[-1]]                 # :342
     assert maxdeg_plus_1 <= 16
-    mtree = merkelize(data, engine=self._engine)                         # :346-348
-    assert mtree[1] == merkle_root
+    assert _host_merkle_root(data) == merkle_root                        # :346-348
     powers = [pow(root, i, p) for i in range(len(data))]
     pts = [x for x in range(len(data)) if x % exclude_multiples_of] if exclude_multiples_of else list(range(len(data)))
     xs = [powers[x] for x in pts[:maxdeg_plus_1]]
@@ -124,6 +123,18 @@ class SmoothSubgroupFRI(object):
     for x in pts[maxdeg_plus_1:]:                                        # :357-362
       assert _lagrange_eval(xs, ys_, powers[x], p) == data[x] % p
     return True
+
+
+def _host_merkle_root(data):
+  """Root of merkelize(data) for the verifier's final check (a few hundred 32-byte leaves:
+  host hashing, like every other verifier step)."""
+  from .merkle_tree import blake, permute4
+  nodes = [x.to_bytes(32, "big") for x in permute4(list(data))]
+  n = len(nodes)
+  tree = [b""] * n + nodes
+  for i in range(n - 1, 0, -1):
+    tree[i] = blake(tree[2 * i] + tree[2 * i + 1])
+  return tree[1]
 
 
 def _lagrange_eval(xs, ys, x, p):

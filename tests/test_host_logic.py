@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic above the C ABI (no GPU): value types, limb conversions,
+Fiat-Shamir helpers, Merkle index arithmetic and the verifier -- exercised on proofs made by
+the CPU oracle."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+P = 2**256 - 351 * 2**32 + 1
+
+
+def test_limbs_roundtrip():
+  from starks_b200.limbs import ints_to_limbs, limbs_to_ints, limbs_to_be_bytes, be_bytes_to_limbs, int_to_limbs
+  vals = [0, 1, P - 1, 2**255 + 12345, 0xdeadbeef << 100]
+  L = ints_to_limbs(vals)
+  assert L.shape == (5, 8) and limbs_to_ints(L) == vals
+  be = limbs_to_be_bytes(L)
+  assert [be[i].tobytes() for i in range(5)] == [v.to_bytes(32, "big") for v in vals]
+  assert (be_bytes_to_limbs(be) == L).all()
+  assert (int_to_limbs(P) == np.array([1, 0xFFFFFEA1] + [0xFFFFFFFF] * 6, dtype=np.uint32)).all()
+
+
+def test_modp_mirror():
+  from starks_b200.modp import IntegersModP
+  F = IntegersModP(P)
+  assert IntegersModP(P) is F
+  a, b = F(2)**256, F(7)
+  assert int(a) == 351 * 2**32 - 1                      # starks/test/test_modpy.py:28-35
+  e = (P - 1) // 2
+  assert int(b**e) == pow(7, e, P) == P - 1            # :54-61
+  assert int(a * b + 1 - b) == (int(a) * 7 + 1 - 7) % P
+  assert int((a / b) * b) == int(a) and int(b.inverse() * b) == 1
+  assert F(b"\xff" * 32).n == 2**256 - 1                # bytes ctor does not reduce (modp.py:33-34)
+  assert b.to_bytes() == (7).to_bytes(32, "big") and isinstance(a + 1, F) and (1 + a) == (a + 1)
+  with pytest.raises(TypeError):
+    F("x")
+
+
+def test_polynomial_mirrors():
+  from starks_b200.modp import IntegersModP
+  from starks_b200.polynomial import polynomials_over, generate_Xi_s, monomials_of
+  F = IntegersModP(31)
+  poly = polynomials_over(F).factory([0, 1, 2, 3, 0, 0])
+  assert [int(c) for c in poly.coefficients] == [0, 1, 2, 3] and poly.degree() == 3
+  assert int(poly(F(2))) == (2 + 8 + 24) % 31
+  assert polynomials_over(F).factory([0, 0]).coefficients == []
+  X = generate_Xi_s(F, 2)
+  sp = X[0] + 2 * X[1]**2
+  assert monomials_of(sp, 2, 31) == [((0, 2), 2), ((1, 0), 1)] and sp.degree() == 2
+  assert int(sp([F(3), F(4)])) == (3 + 2 * 16) % 31
+  assert monomials_of({(1, 1): 34}, 2, 31) == [((1, 1), 3)]
+
+
+def test_utils_host():
+  from starks_b200.utils import multiplicative_order, get_pseudorandom_indices, is_a_power_of_2
+  assert multiplicative_order(pow(3, 5, 31), 31) == 6
+  assert multiplicative_order(pow(7, (P - 1) // 2**20, P), P) == 2**20
+  assert multiplicative_order(1, P) == 1 and multiplicative_order(P - 1, P) == 2
+  g = load_golden("field_utils.json")
+  for e in g["indices"]:
+    assert get_pseudorandom_indices(bytes.fromhex(e["seed"]), e["modulus"], e["count"], e["exclude"]) == e["out"]
+  with pytest.raises(AssertionError):
+    get_pseudorandom_indices(b"\0" * 32, 2**24, 4)
+  assert is_a_power_of_2(64) and not is_a_power_of_2(48)
+  from starks_b200.stark import get_pseudorandom_ks
+  for e in g["ks"]:
+    assert [("%064x" % k) for k in get_pseudorandom_ks(bytes.fromhex(e["root"]), e["num"])] == e["out"]
+  assert get_pseudorandom_ks(b"\0" * 32, 10) is None
+
+
+def test_merkle_host_helpers(oracle):
+  import starks_b200.merkle_tree as mt
+  assert mt.permute4(list(range(8))) == [0, 2, 4, 6, 1, 3, 5, 7]
+  assert mt.permute4([1, 2, 3]) == []
+  t = oracle.merkelize([x.to_bytes(32, "big") for x in range(128)])
+  assert mt.verify_branch(t[1], 59, mt.mk_branch(t, 59), output_as_int=True) == 59
+  with pytest.raises(AssertionError):
+    mt.verify_branch(t[1], 58, mt.mk_branch(t, 59))
+  assert mt.blake(b"abc").hex() == "508c5e8c327c14e2e1a72ba34eeb452f37458b209ed63a294d999b4c86675982"
+  leaf = b"".join(bytes([i]) * 32 for i in range(6))
+  assert mt.unpack_merkle_leaf(leaf, 2, 3) == [bytes([i]) * 32 for i in range(6)]
+
+
+def test_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle):
+  """STARK.verify_proof / FRI.verify_proximity_proof (host mirrors of stark.py:281-372,
+  fri.py:268-366) on proofs produced by the CPU oracle."""
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  from starks_b200.fri import FRI
+  F = IntegersModP(P)
+  sp = [{(0, 1): 1}, {(1, 0): 1, (0, 2): 2}]
+  steps = 64
+  witness = oracle.computational_trace(P, [2, 5], steps, sp)
+  boundary = [(0, 0, 2), (0, 1, 5)]
+  proof = oracle.StarkOracle(steps, 8, 2, sp).mk_proof(witness, boundary)
+  S = STARK(F, steps, 8, 2, sp)
+  assert S.get_degree() == 2
+  assert S.verify_proof(proof, witness, boundary)
+  bad = [proof[0], proof[1], list(proof[2]), proof[3]]
+  leaf = bytearray(bad[2][0][0]); leaf[40] ^= 1
+  bad[2][0] = [bytes(leaf)] + list(bad[2][0][1:])
+  with pytest.raises(AssertionError):
+    S.verify_proof(bad, witness, boundary)
+  # FRI alone
+  n, deg = 1 << 10, 128
+  w = pow(7, (P - 1) // n, P)
+  f = [oracle.synth(9, i) for i in range(deg)]
+  prf = oracle.fri_prove(P, f, w, deg, exclude_multiples_of=8)
+  root = oracle.merkelize(oracle.fft_1d(P, f, w, order=n))[1]
+  assert FRI(F).verify_proximity_proof(prf, root, F(w), deg, exclude_multiples_of=8)
+  with pytest.raises(AssertionError):
+    FRI(F).verify_proximity_proof(prf, b"\1" * 32, F(w), deg, exclude_multiples_of=8)
+
+
+def test_install_rebinds_reference_when_present():
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+  import pyref
+  if not pyref.available():
+    pytest.skip("upstream reference tree not present")
+  pyref.load()
+  import starks.stark, starks.fft, starks.merkle_tree, starks.fri
+  saved = {m: dict(vars(sys.modules[m])) for m in ("starks.fft", "starks.merkle_tree", "starks.fri", "starks.stark", "starks.utils")}
+  saved_mk = starks.stark.STARK.mk_proof
+  try:
+    import starks_b200.install as shim
+    import starks_b200.fft as bfft, starks_b200.merkle_tree as bmt, starks_b200.fri as bfri
+    assert shim.install()
+    assert starks.fft.fft_1d is bfft.fft_1d and starks.merkle_tree.merkelize is bmt.merkelize
+    assert starks.stark.merkelize is bmt.merkelize and starks.stark.FRI is bfri.FRI
+    assert starks.fri.merkelize is bmt.merkelize and starks.fri.SmoothSubgroupFRI is bfri.SmoothSubgroupFRI
+    assert starks.stark.STARK.mk_proof is not saved_mk
+  finally:
+    for m, d in saved.items():
+      vars(sys.modules[m]).update(d)
+    starks.stark.STARK.mk_proof = saved_mk
