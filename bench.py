@@ -81,6 +81,62 @@ def synth_columns(cols, n, seed):
   return a
 
 
+def extras(eng, torch, stream, local):
+  """Second half of BASELINE.json's metric, per GPU: LDE + Merkle commit of 64 trace columns of
+  2^18 steps (config 3; trace resident on the device -> root on the host) and the full
+  Fibonacci proof at 2^20 steps (config 5 shape on one GPU)."""
+  import numpy as np
+  out = {}
+  steps, ext, ncols = 1 << 18, 8, 64
+  n = steps * ext
+  g2 = pow(7, (P - 1) // n, P)
+  d_tr = torch.randint(0, 2**31 - 1, (ncols, steps, 8), dtype=torch.int32, device="cuda:%d" % local)
+  d_ev = torch.empty((ncols, n, 8), dtype=torch.int32, device="cuda:%d" % local)
+  d_nodes = torch.empty((n, 32), dtype=torch.uint8, device="cuda:%d" % local)
+  for _ in range(2):
+    eng.lde_commit(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n, d_nodes.data_ptr())
+  reps = 5
+  t0 = time.perf_counter()
+  for _ in range(reps):
+    root = eng.lde_commit(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n, d_nodes.data_ptr())
+  out["lde_merkle_commit_ms_64x2^18_x8"] = (time.perf_counter() - t0) / reps * 1e3
+  # split: LDE alone / commit alone (CUDA events on the launching stream)
+  e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+  with torch.cuda.stream(stream):
+    e[0].record(stream)
+    eng.lde(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n)
+    e[1].record(stream)
+    eng.merkle_commit(d_ev.data_ptr(), n, ncols, n, d_nodes.data_ptr(), want_root=False)
+    e[2].record(stream)
+  torch.cuda.synchronize()
+  out["lde_ms"] = e[0].elapsed_time(e[1])
+  out["merkle_ms"] = e[1].elapsed_time(e[2])
+  compressions = (n // 2) * ncols + (n // 2 - 1)
+  out["merkle_gcompress_per_s"] = compressions / (out["merkle_ms"] * 1e-3) / 1e9
+  lde_bfly = ncols * ((steps // 2) * 18 + (n // 2) * 21)
+  out["lde_gbutterflies_per_s"] = lde_bfly / (out["lde_ms"] * 1e-3) / 1e9
+  del d_tr, d_ev, d_nodes
+  torch.cuda.empty_cache()
+  # full proof, 2^20 steps
+  from starks_b200.limbs import ints_to_limbs
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  psteps = 1 << 20
+  a, b, c0, c1 = 0, 1, [], []
+  for _ in range(psteps):
+    c0.append(a)
+    c1.append(b)
+    a, b = b, (a + b) % P
+  witness = np.stack([ints_to_limbs(c0), ints_to_limbs(c1)])
+  S = STARK(IntegersModP(P), psteps, 8, 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], engine=eng)
+  S.mk_proof(witness, [(0, 0, 0), (0, 1, 1)])
+  t0 = time.perf_counter()
+  proof = S.mk_proof(witness, [(0, 0, 0), (0, 1, 1)])
+  out["stark_proof_s_fib_2^20_steps_x8"] = time.perf_counter() - t0
+  out["stark_proof_fri_layers"] = len(proof[3])
+  return out
+
+
 def cpu_port_baseline(cols_sample, threads):
   """Times the oracle (C port of starks/fft.py:303-331) on `cols_sample` columns of 2^20."""
   sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -134,6 +190,7 @@ def main():
   ap.add_argument("--cols", type=int, default=64)
   ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-extras", action="store_true", help="skip the LDE+Merkle / full-proof timings")
   args = ap.parse_args()
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,6 +310,11 @@ def main():
     if e2e_s is not None:
       line["e2e"] = {"value": elems / e2e_s / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": cols * N * 32,
                      "d2h_bytes_per_step": cols * N * 32, "ms_per_step": e2e_s * 1e3}
+    if not args.no_extras:
+      try:
+        line["extra"] = extras(eng, torch, stream, local)
+      except Exception as ex:  # pragma: no cover
+        line["extra"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu:
       v, dt = cpu_port_baseline(4, 1)
       line["cpu_baseline"] = {"value": v, "unit": "Melem/s", "cores": 1, "kind": "port",

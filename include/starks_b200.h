@@ -85,6 +85,17 @@ int stk_vec_op(stk_ctx* ctx, int op, const uint32_t* d_a, const uint32_t* d_b, u
 /* get_power_cycle (starks/utils.py:30-38): out[i] = r^i, i < n (n = order of r). */
 int stk_power_cycle(stk_ctx* ctx, const uint32_t r[8], uint64_t n, uint32_t* d_out);
 
+/* One large transform over G = nranks GPUs (four-step, one all-to-all; SURVEY.md App. C.4;
+ * replaces a single fft_1d call, starks/fft.py:316-331, whose column does not fit or is
+ * sharded).  Order N = nranks * local_n.  Input is cyclic (rank r holds x[r + G*m]).
+ *   phase 0: in place, the butterfly levels that stay inside one residue class;
+ *   caller:  all-to-all of equal contiguous chunks, then a local [r][m] -> [m][r] transpose;
+ *   phase 1: the last log2(G) levels + bit-reversed store; rank r' ends with X[K] for
+ *            K mod G = bitrev(r'), at local position K / G. */
+int stk_ntt_dist_phase(stk_ctx* ctx, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n,
+                       uint64_t batch, uint64_t stride, const uint32_t root[8], uint64_t nranks, uint64_t rank,
+                       int inverse);
+
 /* ---- LDE ------------------------------------------------------------------------ */
 /* construct_trace_polynomials + evaluation loop (starks/stark.py:27-36, 254-256): per column
  * inverse NTT of `steps` trace values over <G1>, G1 = g2^ext, then forward NTT of the

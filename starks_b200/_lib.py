@@ -46,6 +46,7 @@ SIGNATURES = {
     "stk_mul_polys": (cint, [vp, vp, u64, vp, u64, vp, u64, u32p]),
     "stk_vec_op": (cint, [vp, cint, vp, vp, vp, u64]),
     "stk_power_cycle": (cint, [vp, u32p, u64, vp]),
+    "stk_ntt_dist_phase": (cint, [vp, cint, vp, vp, u64, u64, u64, u32p, u64, u64, cint]),
     "stk_lde": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, u64]),
     "stk_lde_commit": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, vp]),
     "stk_merkle_commit": (cint, [vp, vp, u64, u64, u64, vp, vp]),

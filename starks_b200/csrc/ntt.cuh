@@ -39,6 +39,13 @@ struct NttPass {
   uint32_t n_in;   // valid input elements per column; above that the input is zero
   uint32_t batch;  // number of columns
   unsigned long long in_col_stride, out_col_stride;  // elements
+  // distributed (multi-GPU four-step) use: the local array holds the elements of a longer
+  // transform of order 2^n_tw whose global index is (J << j_shift) | j_or; the final store
+  // goes to local position bitrev_{n_tw}(global J) >> out_shift.  Single-GPU: n_tw = n, rest 0.
+  int n_tw;
+  int j_shift;
+  uint32_t j_or;
+  int out_shift;
   const fe* in;
   fe* out;
   const fe* W;
@@ -79,15 +86,16 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
       }
     }
     // exponent of the last (smallest-half) level of this round
-    const uint32_t Jl = J0 & ((1u << gshift) - 1u);
-    const uint32_t er = Jl << (A.n - 1 - gshift);
+    const int ggs = gshift + A.j_shift;  // log2 of the global index stride of m
+    const uint32_t Jl = ((J0 << A.j_shift) | A.j_or) & ((1u << ggs) - 1u);
+    const uint32_t er = Jl << (A.n_tw - 1 - ggs);
 #pragma unroll
     for (int lv = 0; lv < R; ++lv) {
       const int lh = R - 1 - lv;  // log2 of half size in m units
       const int hm = 1 << lh;
 #pragma unroll
       for (int mm = 0; mm < hm; ++mm) {
-        const uint32_t e = (er >> lh) + ((uint32_t)mm << (A.n - 1 - lh));
+        const uint32_t e = (er >> lh) + ((uint32_t)mm << (A.n_tw - 1 - lh));
         const fe tw = fe_load_ro(A.W + e);
 #pragma unroll
         for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
@@ -105,7 +113,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
         for (int m = 0; m < M; ++m) {
           uint32_t J = J0 + ((uint32_t)m << gshift);
-          uint32_t K = A.final_pass ? (__brev(J) >> (32 - A.n)) : J;
+          uint32_t K = A.final_pass ? ((__brev((J << A.j_shift) | A.j_or) >> (32 - A.n_tw)) >> A.out_shift) : J;
           fe v = x[m];
           if (A.do_scale) v = f.mul_tw(v, A.scale);
           fe_store(dst + K, v);
@@ -122,8 +130,8 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
   }
 }
 
-template <class F, int MAXR>
-__global__ void __launch_bounds__(4096 >> MAXR, 1) ntt_pass_kernel(const NttPass A, const F f) {
+template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, const F f) {
   extern __shared__ uint32_t sm[];
   const uint32_t T = 1u << A.logT;
   const uint32_t xb = blockIdx.x;

@@ -207,7 +207,7 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
   if (n <= kmax) {
     NttPass P;
     memset(&P, 0, sizeof P);
-    P.n = n; P.lo = 0; P.k = n;
+    P.n = n; P.n_tw = n; P.lo = 0; P.k = n;
     P.logC = std::min(logT - n, ilog2_u64(batch));
     P.logT = P.k + P.logC;
     P.c_is_col = 1; P.cb = 0; P.nl = 0; P.sl = 0; P.sh = 0;
@@ -222,7 +222,7 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
     int k = (hi + (npass - i) - 1) / (npass - i);  // spread the remaining bits evenly
     NttPass P;
     memset(&P, 0, sizeof P);
-    P.n = n; P.k = k; P.lo = hi - k;
+    P.n = n; P.n_tw = n; P.k = k; P.lo = hi - k;
     P.final_pass = (i == npass - 1);
     P.c_is_col = 0;
     P.logC = logT - k;
@@ -243,11 +243,12 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
   return STK_OK;
 }
 
-template <class F, int MAXR>
+template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1>
 static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
   static bool attr_done = false;
   if (!attr_done) {
-    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MAXT == 128 ? 32 * 1024 : 200 * 1024));
     attr_done = true;
   }
   const uint32_t T = 1u << P.logT;
@@ -257,14 +258,22 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
   dim3 grid((unsigned)tiles, (unsigned)cols);
   size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
-  ntt_pass_kernel<F, MAXR><<<grid, threads, smem, s>>>(P, f);
+  ntt_pass_kernel<F, MAXR, MAXT, MINB><<<grid, threads, smem, s>>>(P, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }
 
 template <class F>
 static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
-  if (ntt_max_radix() >= 3) return launch_pass_r<F, 3>(c, s, P, f);
+  if (ntt_max_radix() >= 3) {
+    if (P.logT <= 10) {  // 128-thread tiles: trade registers for resident CTAs
+      const int minb = env_int("STK_NTT_MINB", 4);
+      if (minb >= 6) return launch_pass_r<F, 3, 128, 6>(c, s, P, f);
+      if (minb == 5) return launch_pass_r<F, 3, 128, 5>(c, s, P, f);
+      return launch_pass_r<F, 3, 128, 4>(c, s, P, f);
+    }
+    return launch_pass_r<F, 3>(c, s, P, f);
+  }
   return launch_pass_r<F, 2>(c, s, P, f);
 }
 
@@ -434,6 +443,77 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_host(stk_ctx* c, c
   }
   STK_CUDA(c, cudaStreamSynchronize(c->copy_streams[0]));
   STK_CUDA(c, cudaStreamSynchronize(c->copy_streams[1]));
+  return STK_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU four-step phases
+// A transform of order N = G * L over G ranks, one all-to-all:
+//   input   cyclic: rank r holds x[r + G*m], m < L
+//   phase 0 (in place, no communication): the top log2(L) butterfly levels of the DIF act inside
+//           one residue class r -- a partial transform of the local array whose global index
+//           is (m << g) | r;
+//   all-to-all + local transpose (done by the caller): rank r' then holds the block
+//           J in [r'*L, (r'+1)*L) of the partially transformed global array, low g bits fastest;
+//   phase 1: the last g = log2(G) levels and the bit-reversed store; the output index K has
+//           K mod G = bitrev_g(r'), and rank r' keeps X[K] at local position K >> g
+//           (cyclic output, k2-sharded as in App. C.4).
+extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
+    stk_ctx* c, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n, uint64_t batch, uint64_t stride,
+    const uint32_t root[8], uint64_t nranks, uint64_t rank, int inverse) {
+  if (!c || !d_in || !d_out || !root || local_n == 0 || batch == 0) return STK_EINVAL;
+  if ((local_n & (local_n - 1)) || (nranks & (nranks - 1)) || nranks < 2 || rank >= nranks || nranks > 8)
+    return stk_fail(c, STK_EINVAL, "local length and rank count must be powers of two (2..8 ranks)");
+  if (phase != 0 && phase != 1) return STK_EINVAL;
+  const int nloc = ilog2_u64(local_n), g = ilog2_u64(nranks), n = nloc + g;
+  if (n > 30 || nloc < 3) return stk_fail(c, STK_EUNSUPPORTED, "distributed transform needs 2^3 <= local length and N <= 2^30");
+  if (phase == 0 && d_in != d_out) return stk_fail(c, STK_EINVAL, "phase 0 works in place");
+  if (phase == 1 && (const void*)d_in == (const void*)d_out) return stk_fail(c, STK_EINVAL, "phase 1 works out of place");
+  fe r = stk_load_fe(root);
+  const uint64_t N = local_n * nranks;
+  fe one = host::reduce(host::from_u64(1), c->p);
+  if (!fe_eq(stk_h_pow(c, r, N), one) || fe_eq(stk_h_pow(c, r, N / 2), one))
+    return stk_fail(c, STK_EINVAL, "root is not a primitive (G*L)-th root of unity");
+  fe w = inverse ? stk_h_inv(c, r) : r;
+  const fe* W = nullptr;
+  STK_TRY(stk_get_table(c, w, N, &W));
+  std::vector<NttPass> plan;
+  if (phase == 0) {
+    STK_TRY(build_plan(nloc, batch, plan));
+    for (auto& P : plan) {
+      P.final_pass = 0;  // keep the tile geometry, store in place
+      P.n_tw = n; P.j_shift = g; P.j_or = (uint32_t)rank; P.out_shift = 0;
+    }
+  } else {
+    // last g levels: bits [0, g) of the local index; final-pass geometry (batch bits on top)
+    const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 10)));
+    NttPass P;
+    memset(&P, 0, sizeof P);
+    P.n = nloc; P.k = g; P.lo = 0; P.final_pass = 1; P.c_is_col = 0;
+    P.logC = std::min(logT - g, nloc - g);
+    P.cb = nloc - P.logC;
+    P.nl = nloc - P.logC - g; P.sl = g; P.sh = 0;
+    P.logT = P.k + P.logC;
+    fill_rounds(P);
+    P.n_tw = n; P.j_shift = 0; P.j_or = (uint32_t)(rank << nloc); P.out_shift = g;
+    plan.push_back(P);
+  }
+  fe scale_tw = fe_zero();
+  int do_scale = 0;
+  if (inverse && phase == 1) {
+    scale_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(N), c->p)));
+    do_scale = 1;
+  }
+  for (auto& P : plan) {
+    P.batch = (uint32_t)batch;
+    P.W = W;
+    P.n_in = (uint32_t)local_n;
+    P.in = (const fe*)d_in; P.in_col_stride = stride;
+    P.out = (fe*)d_out; P.out_col_stride = stride;
+    P.do_scale = (P.final_pass && do_scale) ? 1 : 0;
+    P.scale = scale_tw;
+    if (c->is_stark) STK_TRY(launch_pass<StarkField>(c, c->stream, P, StarkField()));
+    else STK_TRY(launch_pass<MontField>(c, c->stream, P, c->mont));
+  }
   return STK_OK;
 }
 

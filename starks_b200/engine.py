@@ -135,6 +135,12 @@ class Engine:
                                       _u32(int_to_limbs(int(root) % self.p)), int(bool(inverse))))
     return out
 
+  def ntt_dist_phase(self, phase, d_in, d_out, local_n, batch, stride, root, nranks, rank, inverse=False):
+    """One phase of the multi-GPU four-step transform (stk_ntt_dist_phase)."""
+    self._check(self.lib.stk_ntt_dist_phase(self.ctx, int(phase), d_in, d_out, local_n, batch, stride,
+                                            _u32(int_to_limbs(int(root) % self.p)), nranks, rank,
+                                            int(bool(inverse))))
+
   def mul_polys(self, a, b, n, root):
     a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 8)
     b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 8)
