@@ -33,14 +33,67 @@ inline fe reduce(const fe& x, const fe& p) {
   }
   return r;
 }
-// a*b mod p, double-and-add (256 iterations), a,b < p.
-inline fe mulmod(const fe& a, const fe& b, const fe& p) {
-  fe r = fe_zero();
-  for (int i = 255; i >= 0; --i) {
-    r = addmod(r, r, p);
-    if ((b.v[i >> 5] >> (i & 31)) & 1u) r = addmod(r, a, p);
-  }
+// 4x64-limb Montgomery context for the host (per modulus, cached thread-locally).
+struct HostMont {
+  fe p;
+  uint64_t m[4];    // modulus
+  uint64_t r2[4];   // 2^512 mod p
+  uint64_t ninv;    // -p^-1 mod 2^64
+  bool valid = false;
+};
+inline void to64(const fe& a, uint64_t* o) {
+  for (int i = 0; i < 4; ++i) o[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+inline fe from64(const uint64_t* a) {
+  fe r;
+  for (int i = 0; i < 4; ++i) { r.v[2 * i] = (uint32_t)a[i]; r.v[2 * i + 1] = (uint32_t)(a[i] >> 32); }
   return r;
+}
+inline void mont64(const HostMont& H, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  typedef unsigned __int128 u128;
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    u128 c = 0;
+    for (int j = 0; j < 4; ++j) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t mm = t[0] * H.ninv;
+    c = (u128)mm * H.m[0] + t[0]; c >>= 64;
+    for (int j = 1; j < 4; ++j) { c += (u128)mm * H.m[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  bool ge = t[4] != 0;
+  if (!ge) {
+    ge = true;
+    for (int i = 3; i >= 0; --i) { if (t[i] > H.m[i]) break; if (t[i] < H.m[i]) { ge = false; break; } }
+  }
+  if (ge) {
+    uint64_t bw = 0;
+    for (int i = 0; i < 4; ++i) { u128 d = (u128)t[i] - H.m[i] - bw; t[i] = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1; }
+  }
+  for (int i = 0; i < 4; ++i) out[i] = t[i];
+}
+inline const HostMont& host_mont(const fe& p) {
+  static thread_local HostMont H;
+  if (H.valid && fe_eq(H.p, p)) return H;
+  H.p = p;
+  to64(p, H.m);
+  uint64_t inv = 1;
+  for (int i = 0; i < 6; ++i) inv *= 2 - H.m[0] * inv;
+  H.ninv = (uint64_t)0 - inv;
+  fe x = from_u64(1);
+  for (int i = 0; i < 512; ++i) x = addmod(x, x, p);
+  to64(x, H.r2);
+  H.valid = true;
+  return H;
+}
+// a*b mod p (p odd), a, b < p: mont(mont(a, b), R^2) = a*b
+inline fe mulmod(const fe& a, const fe& b, const fe& p) {
+  const HostMont& H = host_mont(p);
+  uint64_t x[4], y[4], t[4];
+  to64(a, x); to64(b, y);
+  mont64(H, x, y, t);
+  mont64(H, t, H.r2, t);
+  return from64(t);
 }
 inline fe powmod(const fe& a, const fe& e, const fe& p) {
   fe r = reduce(from_u64(1), p);

@@ -248,7 +248,7 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   static bool attr_done = false;
   if (!attr_done) {
     STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     MAXT == 128 ? 32 * 1024 : 200 * 1024));
+                                     MAXT <= 256 ? 32 * 1024 : 200 * 1024));
     attr_done = true;
   }
   const uint32_t T = 1u << P.logT;
@@ -273,6 +273,12 @@ static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f)
       return launch_pass_r<F, 3, 128, 4>(c, s, P, f);
     }
     return launch_pass_r<F, 3>(c, s, P, f);
+  }
+  if (P.logT <= 10) {  // radix-4 rounds, 256-thread tiles
+    const int minb = env_int("STK_NTT_MINB", 3);
+    if (minb >= 4) return launch_pass_r<F, 2, 256, 4>(c, s, P, f);
+    if (minb == 3) return launch_pass_r<F, 2, 256, 3>(c, s, P, f);
+    return launch_pass_r<F, 2, 256, 2>(c, s, P, f);
   }
   return launch_pass_r<F, 2>(c, s, P, f);
 }

@@ -15,17 +15,30 @@ P_STARK = 2**256 - 351 * 2**32 + 1
 
 
 class DevBuf:
-  """A device allocation made through stk_dev_alloc."""
+  """A device allocation made through stk_dev_alloc.  Freed buffers go back to a per-engine
+  pool keyed by (rounded) size: cudaMalloc/cudaFree of GiB-sized buffers cost milliseconds and
+  cudaFree synchronises the device, which would dominate a 20 ms proof.  Reuse is safe because
+  every kernel of an engine runs on one stream (stream order = reuse order)."""
+
+  _GRAN = 1 << 16
 
   def __init__(self, eng, nbytes):
     self.eng, self.nbytes = eng, int(nbytes)
+    self.cap = max(self._GRAN, (self.nbytes + self._GRAN - 1) // self._GRAN * self._GRAN)
+    pool = eng._pool.get(self.cap)
+    if pool:
+      self.ptr = pool.pop()
+      return
     p = ctypes.c_void_p()
-    eng._check(eng.lib.stk_dev_alloc(eng.ctx, self.nbytes, ctypes.byref(p)))
+    rc = eng.lib.stk_dev_alloc(eng.ctx, self.cap, ctypes.byref(p))
+    if rc != 0:  # out of memory: drop the pool and retry once
+      eng.release_pool()
+      eng._check(eng.lib.stk_dev_alloc(eng.ctx, self.cap, ctypes.byref(p)))
     self.ptr = p.value
 
   def free(self):
     if self.ptr is not None and self.eng.ctx is not None:
-      self.eng.lib.stk_dev_free(self.eng.ctx, self.ptr)
+      self.eng._pool.setdefault(self.cap, []).append(self.ptr)
     self.ptr = None
 
   def __del__(self):
@@ -84,9 +97,18 @@ class Engine:
     self.ctx = ctx
     self.device = device
     self.p = P_STARK
+    self._pool = {}
+
+  def release_pool(self):
+    """Returns pooled device buffers to the driver."""
+    for ptrs in self._pool.values():
+      for p in ptrs:
+        self.lib.stk_dev_free(self.ctx, p)
+    self._pool = {}
 
   def close(self):
     if self.ctx is not None:
+      self.release_pool()
       self.lib.stk_destroy(self.ctx)
       self.ctx = None
 

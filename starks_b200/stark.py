@@ -85,6 +85,8 @@ class STARK(object):
   def mk_proof(self, witness, boundary, keep_device=False):
     """stark.py:233-279."""
     t_start = time.time()
+    marks = [("start", t_start)]
+    mark = lambda name: marks.append((name, time.time()))
     eng = self._engine or default_engine()
     p = self.field.p
     eng.set_field(p)
@@ -98,6 +100,7 @@ class STARK(object):
     d_cols = eng.alloc(3 * w * N * E)        # rows: P_1..P_w, D_1..D_w, B_1..B_w (stark.py:247)
     d_t1 = eng.alloc(w * N * E)
     d_t2 = eng.alloc(w * N * E)
+    mark("upload")
     # construct_trace_polynomials (:27-36) + evaluation (:254-256)
     eng.lde(d_trace.ptr, steps, steps, ext, w, G2, d_cols.ptr, N, d_coeffs=d_pcoef.ptr, coeff_stride=steps)
     # construct_constraint_polynomials (:38-55), evaluation form
@@ -140,9 +143,11 @@ class STARK(object):
       eng.sync()
       d_i.free()
     eng.ntt(d_t2.ptr, steps - 2, steps, d_cols.at(2 * w * N * E), N, N, w, G2)
+    mark("enqueue_polys")
     # merkelize_polynomial_evaluations (:257)
     d_mnodes = eng.alloc(32 * N)
     m_root = eng.merkle_commit(d_cols.ptr, N, 3 * w, N, d_mnodes.ptr)
+    mark("m_root")
     # compute_pseudorandom_linear_combination (:130-177), evaluation form
     k1, k2, k3, k4 = get_pseudorandom_ks(m_root, 4)
     l_ks = get_pseudorandom_ks(m_root, w)
@@ -158,6 +163,7 @@ class STARK(object):
     eng._check(eng.lib.stk_lincomb(eng.ctx, d_cols.ptr, N, 3 * w, N, weights.ctypes.data, d_l.ptr))
     d_lnodes = eng.alloc(32 * N)
     l_root = eng.merkle_commit(d_l.ptr, N, 1, N, d_lnodes.ptr)           # :262-263
+    mark("l_root")
     # compute_merkle_spot_checks (:390-402), samples = 80
     positions = get_pseudorandom_indices(l_root, N, 80, exclude_multiples_of=ext)
     mb = eng.merkle_paths(d_cols.ptr, N, 3 * w, N, d_mnodes.ptr,
@@ -166,12 +172,16 @@ class STARK(object):
     branches = []
     for i in range(len(positions)):
       branches += [mb[2 * i], mb[2 * i + 1], lb[i]]
+    mark("spot_checks")
     # FRI on l (:267-276); its first layer's tree is l_mtree
     fri = FRI(self.field, engine=eng)
     fri_proof = fri.prove_from_device(DeviceLayer(eng, d_l.ptr, N, d_lnodes.ptr, l_root), G2,
                                       steps * self.get_degree(), exclude_multiples_of=ext)
     proof = [m_root, l_root, branches, fri_proof]
-    self.timings["mk_proof_s"] = time.time() - t_start
+    mark("fri")
+    self.timings = {"mk_proof_s": time.time() - t_start}
+    for (a, ta), (b, tb) in zip(marks[:-1], marks[1:]):
+      self.timings[b + "_ms"] = (tb - ta) * 1e3
     if keep_device:
       self.device = dict(cols=d_cols, pcoef=d_pcoef, l=d_l, mnodes=d_mnodes, lnodes=d_lnodes)
     else:
