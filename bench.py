@@ -30,6 +30,9 @@ LOGN = 20
 N = 1 << LOGN
 INT_OPS_PER_BUTTERFLY = 264       # SURVEY.md 8(d), frozen
 BYTES_PER_ELEM = 64               # read once + write once
+# measured once per change with ncu (profiles/r01_ncu_ntt_pass_summary.txt): the two passes of
+# one step move 4.43 GB and 4.24 GB; each pass reads and writes the whole 2 GiB batch
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 4.34e9
 
 
 def peaks():
@@ -297,7 +300,8 @@ def main():
         "clocks": clocks,
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_ntt_pass_summary.txt",
+                     "alg_bytes_per_launch": alg_bytes / launches_per_step, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                      "kernel": "ntt_pass_kernel<StarkField>", "launches_per_step": launches_per_step,
                      "alg_bytes_per_step": alg_bytes},
         "int_roofline": {"bound": "int32 pipes", "alg_int32_ops_per_step": int_ops,

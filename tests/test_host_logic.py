@@ -137,3 +137,25 @@ def test_install_rebinds_reference_when_present():
     for m, d in saved.items():
       vars(sys.modules[m]).update(d)
     starks.stark.STARK.mk_proof = saved_mk
+
+
+def test_compression_mirror(oracle):
+  """starks/compression.py mirror vs values produced by the reference's own functions
+  (tests/golden/compression.json) on oracle-made proofs; round trips as upstream asserts."""
+  from starks_b200.compression import (compress_fri, decompress_fri, compress_branches, decompress_branches,
+                                       bin_length)
+  g = load_golden("compression.json")
+  n, deg = 1 << 10, 128
+  w = pow(7, (P - 1) // n, P)
+  prf = oracle.fri_prove(P, [oracle.synth(9, i) for i in range(deg)], w, deg, exclude_multiples_of=8)
+  c = compress_fri(prf)
+  e = g["fri_2^10"]
+  assert (len(c), bin_length(c), hashlib.blake2s(b"|".join(c)).hexdigest()) == (e["n_objects"], e["bin_length"], e["digest"])
+  assert decompress_fri(c) == prf and bin_length(c) > 0          # test_compression.py:18-42
+  sp = [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]
+  wit = oracle.computational_trace(P, [0, 1], 32, sp)
+  proof = oracle.StarkOracle(32, 8, 2, sp).mk_proof(wit, [(0, 0, 0), (0, 1, 1)])
+  cb = compress_branches(proof[2])
+  e = g["stark_fib32_branches"]
+  assert (len(cb), bin_length(cb), hashlib.blake2s(b"|".join(cb)).hexdigest()) == (e["n_objects"], e["bin_length"], e["digest"])
+  assert decompress_branches(cb) == proof[2]
