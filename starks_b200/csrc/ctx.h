@@ -20,15 +20,15 @@ struct stk_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_streams[2] = {nullptr, nullptr};
+  cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev[8] = {};
   int sm_count = 148;
   bool is_stark = true;
   stk::fe p;
   stk::MontField mont;
   std::vector<stk_table> tables;
-  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-  uint64_t scratch_bytes[4] = {0, 0, 0, 0};
+  void* scratch[8] = {};
+  uint64_t scratch_bytes[8] = {};
   std::string err;
 };
 
