@@ -7,8 +7,8 @@
 //
 // Factorisation used here: plain decimation-in-frequency over the global index J
 // (n = log2 N bits), cut into 1-3 passes.  A pass owns `k` consecutive index bits
-// [lo, lo+k); a CTA stages a tile of C * 2^k elements in shared memory (eight limb planes,
-// XOR-swizzled so every radix-8 round is bank-conflict free), runs the k butterfly levels
+// [lo, lo+k); a CTA stages a tile of C * 2^k elements in shared memory (two planes of
+// 16-byte half-elements, XOR-swizzled so every radix-8 round is bank-conflict free), runs the k butterfly levels
 // as in-register radix-8 (2^R) rounds -- the first round reads global memory directly, the
 // last one writes it directly -- and the final pass stores to the bit-reversed index, which
 // makes the output natural-order without a separate permutation pass.  The C "batch"
@@ -52,7 +52,11 @@ struct NttPass {
   fe scale;  // twiddle form
 };
 
-__device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >> 3) & 31u); }
+// Shared-memory tile: two planes of 16-byte half-elements (limbs 0-3, limbs 4-7), accessed with
+// LDS.128 / STS.128.  A 128-bit access is served per quarter-warp, so eight consecutive lanes
+// must hit eight different 16-byte bank groups; XOR-ing position bits [3,6) into [0,3) does
+// that for every radix-8 round (consecutive lanes differ in bits [0,q) and [q+3, ...)).
+__device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >> 3) & 7u); }
 
 template <class F, int R>
 __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
@@ -63,6 +67,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
   const uint32_t Cm = (1u << A.logC) - 1u;
   const uint32_t ngroups = T >> R;
   const int gshift = A.lo + a;  // global index stride of m is 2^gshift
+  uint4* sm4 = reinterpret_cast<uint4*>(sm);
   for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
     const uint32_t pos0 = ((g >> logS) << (logS + R)) | (g & (S - 1u));
     const uint32_t j0 = pos0 >> A.logC, c0 = pos0 & Cm;
@@ -81,8 +86,9 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         uint32_t ph = sm_phys(pos0 + (uint32_t)m * S);
-#pragma unroll
-        for (int l = 0; l < 8; ++l) x[m].v[l] = sm[l * T + ph];
+        uint4 lo = sm4[ph], hi = sm4[T + ph];
+        x[m].v[0] = lo.x; x[m].v[1] = lo.y; x[m].v[2] = lo.z; x[m].v[3] = lo.w;
+        x[m].v[4] = hi.x; x[m].v[5] = hi.y; x[m].v[6] = hi.z; x[m].v[7] = hi.w;
       }
     }
     // exponent of the last (smallest-half) level of this round
@@ -123,8 +129,8 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         uint32_t ph = sm_phys(pos0 + (uint32_t)m * S);
-#pragma unroll
-        for (int l = 0; l < 8; ++l) sm[l * T + ph] = x[m].v[l];
+        sm4[ph] = make_uint4(x[m].v[0], x[m].v[1], x[m].v[2], x[m].v[3]);
+        sm4[T + ph] = make_uint4(x[m].v[4], x[m].v[5], x[m].v[6], x[m].v[7]);
       }
     }
   }
@@ -132,7 +138,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 
 template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1>
 __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, const F f) {
-  extern __shared__ uint32_t sm[];
+  extern __shared__ __align__(16) uint32_t sm[];
   const uint32_t T = 1u << A.logT;
   const uint32_t xb = blockIdx.x;
   const uint32_t Jcta = ((xb & ((1u << A.nl) - 1u)) << A.sl) | ((xb >> A.nl) << A.sh);
