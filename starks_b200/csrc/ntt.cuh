@@ -42,6 +42,10 @@ struct NttPass {
   // distributed (multi-GPU four-step) use: the local array holds the elements of a longer
   // transform of order 2^n_tw whose global index is (J << j_shift) | j_or; the final store
   // goes to local position bitrev_{n_tw}(global J) >> out_shift.  Single-GPU: n_tw = n, rest 0.
+  // zero-padded inputs (LDE): butterfly levels whose half-size is >= 2^zbit see a structurally
+  // zero second operand, (a, 0) -> (a, a*w), and a zero first operand outside the low 2^zbit
+  // residues; those levels skip the add/sub and the dead multiplies.  zbit = 32 disables it.
+  int zbit;
   int n_tw;
   int j_shift;
   uint32_t j_or;
@@ -58,7 +62,7 @@ struct NttPass {
 // that for every radix-8 round (consecutive lanes differ in bits [0,q) and [q+3, ...)).
 __device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >> 3) & 7u); }
 
-template <class F, int R>
+template <class F, int R, bool ZS>
 __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
                                           uint32_t Jcta, uint32_t col0, int a, bool first, bool last) {
   constexpr int M = 1 << R;
@@ -106,10 +110,16 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
         for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
           const int i0 = blk * 2 * hm + mm, i1 = i0 + hm;
-          fe s = f.add(x[i0], x[i1]);
-          fe d = f.sub(x[i0], x[i1]);
-          x[i0] = s;
-          x[i1] = f.mul_tw(d, tw);
+          if (ZS && gshift + lh >= A.zbit) {
+            // x[i1] == 0 here; x[i0] != 0 only in the low 2^zbit residues mod 2H
+            const uint32_t res = (J0 + ((uint32_t)i0 << gshift)) & ((2u << (gshift + lh)) - 1u);
+            if (res < (1u << A.zbit)) x[i1] = f.mul_tw(x[i0], tw);
+          } else {
+            fe s = f.add(x[i0], x[i1]);
+            fe d = f.sub(x[i0], x[i1]);
+            x[i0] = s;
+            x[i1] = f.mul_tw(d, tw);
+          }
         }
       }
     }
@@ -136,7 +146,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
   }
 }
 
-template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1>
+template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, bool ZS = false>
 __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, const F f) {
   extern __shared__ __align__(16) uint32_t sm[];
   const uint32_t T = 1u << A.logT;
@@ -148,9 +158,9 @@ __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, c
     const int r = A.r[rd];
     a -= r;
     const bool first = rd == 0, last = rd == A.nrounds - 1;
-    if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2)>(A, f, sm, T, Jcta, col0, a, first, last);
-    else if (r == 2) ntt_round<F, 2>(A, f, sm, T, Jcta, col0, a, first, last);
-    else ntt_round<F, 1>(A, f, sm, T, Jcta, col0, a, first, last);
+    if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2), ZS>(A, f, sm, T, Jcta, col0, a, first, last);
+    else if (r == 2) ntt_round<F, 2, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
+    else ntt_round<F, 1, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
     if (!last) __syncthreads();
   }
 }

@@ -243,11 +243,11 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
   return STK_OK;
 }
 
-template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1>
+template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, bool ZS = false>
 static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
   static bool attr_done = false;
   if (!attr_done) {
-    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MAXT <= 256 ? 32 * 1024 : 200 * 1024));
     attr_done = true;
   }
@@ -258,7 +258,7 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
   dim3 grid((unsigned)tiles, (unsigned)cols);
   size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
-  ntt_pass_kernel<F, MAXR, MAXT, MINB><<<grid, threads, smem, s>>>(P, f);
+  ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS><<<grid, threads, smem, s>>>(P, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }
@@ -268,6 +268,7 @@ static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f)
   if (ntt_max_radix() >= 3) {
     if (P.logT <= 10) {  // 128-thread tiles: trade registers for resident CTAs
       const int minb = env_int("STK_NTT_MINB", 4);
+      if (P.zbit < 32) return launch_pass_r<F, 3, 128, 4, true>(c, s, P, f);
       if (minb >= 6) return launch_pass_r<F, 3, 128, 6>(c, s, P, f);
       if (minb == 5) return launch_pass_r<F, 3, 128, 5>(c, s, P, f);
       return launch_pass_r<F, 3, 128, 4>(c, s, P, f);
@@ -363,6 +364,11 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     P.W = W;
     P.do_scale = (P.final_pass && do_scale) ? 1 : 0;
     P.scale = scale_tw;
+    P.zbit = 32;
+    if (i == 0 && n_in > 0 && n_in * 2 <= n && env_int("STK_NTT_ZSKIP", 1)) {
+      int zb = ilog2_u64(n_in);             // 2^zb >= n_in
+      if (zb < P.lo + P.k) P.zbit = zb;     // some level of this pass has half-size >= 2^zb
+    }
     if (plan.size() == 1) {
       if (need_tmp) {  // in place: stage the input
         for (uint64_t b = 0; b < batch; ++b)
@@ -519,6 +525,7 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
   for (auto& P : plan) {
     P.batch = (uint32_t)batch;
     P.W = W;
+    P.zbit = 32;
     P.n_in = (uint32_t)local_n;
     P.in = (const fe*)d_in; P.in_col_stride = stride;
     P.out = (fe*)d_out; P.out_col_stride = stride;
