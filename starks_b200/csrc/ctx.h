@@ -59,6 +59,10 @@ static inline int stk_fail(stk_ctx* c, int code, const char* fmt, ...) {
 // internal helpers (ntt_api.cu)
 int stk_scratch(stk_ctx* c, int slot, uint64_t bytes, void** out);
 int stk_get_table(stk_ctx* c, const stk::fe& root, uint64_t n, const stk::fe** d_table);
+// Same, but may return a longer cached table T (order n*stride, T.root^stride == root) to be
+// indexed as T[e*stride]: sub-transforms (G1 = G2^ext, FRI layers' roots w^4, w^16, ...)
+// reuse the big table instead of building and caching their own.
+int stk_get_table_strided(stk_ctx* c, const stk::fe& root, uint64_t n, const stk::fe** d_table, uint64_t* stride);
 stk::fe stk_load_fe(const uint32_t* w);
 int stk_ntt_dev(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, stk::fe* d_out,
                 uint64_t out_stride, uint64_t n, uint64_t batch, const stk::fe& root, int inverse, int scale);

@@ -16,7 +16,7 @@ namespace {
 
 template <class F>
 __global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ vals, uint64_t q,
-                                                        const fe* __restrict__ Winv, fe x_plain, fe iota_tw,
+                                                        const fe* __restrict__ Winv, uint64_t wstride, fe x_plain, fe iota_tw,
                                                         fe quarter_tw, fe* __restrict__ out, const F f) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= q) return;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ v
   fe m = f.mul_tw(d13, iota_tw);
   fe c0 = f.add(s02, s13), c2 = f.sub(s02, s13);  // 4*b0, 4*b2
   fe c1 = f.sub(d02, m), c3 = f.add(d02, m);      // 4*b1, 4*b3
-  fe t = f.mul_tw(x_plain, fe_load_ro(Winv + i));  // x * w^-i, plain
+  fe t = f.mul_tw(x_plain, fe_load_ro(Winv + i * wstride));  // x * w^-i, plain
   fe t_tw = f.to_tw(t);
   fe r = f.add(f.mul_tw(c3, t_tw), c2);
   r = f.add(f.mul_tw(r, t_tw), c1);
@@ -47,16 +47,17 @@ extern "C" __attribute__((visibility("default"))) int stk_fri_fold4(stk_ctx* c, 
     return stk_fail(c, STK_EINVAL, "root is not a primitive n-th root of unity");
   fe winv = stk_h_inv(c, w);
   const fe* Winv;
-  STK_TRY(stk_get_table(c, winv, n, &Winv));
+  uint64_t wstride = 1;
+  STK_TRY(stk_get_table_strided(c, winv, n, &Winv, &wstride));
   fe x = host::reduce(stk_load_fe(special_x), c->p);  // fri.py:229 does not reduce; products do
   fe iota_tw = stk_h_to_tw(c, stk_h_pow(c, w, q));
   fe quarter_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(4), c->p)));
   unsigned blocks = (unsigned)((q + 255) / 256);
   if (c->is_stark)
-    fri_fold4_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, x, iota_tw, quarter_tw,
+    fri_fold4_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, wstride, x, iota_tw, quarter_tw,
                                                                 (fe*)d_out, StarkField());
   else
-    fri_fold4_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, x, iota_tw, quarter_tw,
+    fri_fold4_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, wstride, x, iota_tw, quarter_tw,
                                                                (fe*)d_out, c->mont);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;

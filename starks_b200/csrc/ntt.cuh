@@ -46,6 +46,7 @@ struct NttPass {
   // zero second operand, (a, 0) -> (a, a*w), and a zero first operand outside the low 2^zbit
   // residues; those levels skip the add/sub and the dead multiplies.  zbit = 32 disables it.
   int zbit;
+  int tw_shift;  // the table is a longer one: entry e lives at W[e << tw_shift]
   int n_tw;
   int j_shift;
   uint32_t j_or;
@@ -106,7 +107,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
       for (int mm = 0; mm < hm; ++mm) {
         const uint32_t e = (er >> lh) + ((uint32_t)mm << (A.n_tw - 1 - lh));
-        const fe tw = fe_load_ro(A.W + e);
+        const fe tw = fe_load_ro(A.W + ((unsigned long long)e << A.tw_shift));
 #pragma unroll
         for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
           const int i0 = blk * 2 * hm + mm, i1 = i0 + hm;

@@ -160,7 +160,7 @@ extern "C" __attribute__((visibility("default"))) int stk_memset(stk_ctx* c, voi
 int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
   for (auto& t : c->tables)
     if (t.n == n && fe_eq(t.root, root)) { *d_table = t.d; return STK_OK; }
-  if (c->tables.size() >= 24) {  // bounded cache: drop the oldest
+  if (c->tables.size() >= 48) {  // bounded cache: drop the oldest
     STK_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->tables.front().d);
     c->tables.erase(c->tables.begin());
@@ -183,6 +183,19 @@ int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
   c->tables.push_back(t);
   *d_table = t.d;
   return STK_OK;
+}
+
+int stk_get_table_strided(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table, uint64_t* stride) {
+  *stride = 1;
+  for (auto& t : c->tables)
+    if (t.n == n && fe_eq(t.root, root)) { *d_table = t.d; return STK_OK; }
+  for (auto& t : c->tables) {
+    if (t.n > n && t.n % n == 0) {
+      uint64_t s = t.n / n;
+      if (fe_eq(stk_h_pow(c, t.root, s), root)) { *d_table = t.d; *stride = s; return STK_OK; }
+    }
+  }
+  return stk_get_table(c, root, n, d_table);
 }
 
 // ------------------------------------------------------------------ NTT plan
@@ -287,7 +300,8 @@ static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f)
 // direct DFT for orders that are not a power of two >= 8 (_simple_ft, starks/fft.py:287-300)
 template <class F>
 __global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stride, fe* out, uint64_t out_stride,
-                                   uint64_t n, uint64_t batch, const fe* W, int do_scale, fe scale, const F f) {
+                                   uint64_t n, uint64_t batch, const fe* W, uint64_t wstride, int do_scale, fe scale,
+                                   const F f) {
   uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (idx >= n * batch) return;
   uint64_t k = idx % n, col = idx / n;
@@ -295,7 +309,7 @@ __global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stri
   fe acc = fe_zero();
   for (uint64_t j = 0; j < n_in; ++j) {
     uint64_t e = (j * k) % n;
-    acc = f.add(acc, f.mul_tw(fe_load(src + j), fe_load_ro(W + e)));
+    acc = f.add(acc, f.mul_tw(fe_load(src + j), fe_load_ro(W + e * wstride)));
   }
   if (do_scale) acc = f.mul_tw(acc, scale);
   fe_store(out + col * out_stride + k, acc);
@@ -317,7 +331,8 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   }
   fe w = inverse ? stk_h_inv(c, root) : root;
   const fe* W = nullptr;
-  STK_TRY(stk_get_table(c, w, n, &W));
+  uint64_t wstride = 1;
+  STK_TRY(stk_get_table_strided(c, w, n, &W, &wstride));
   fe scale_tw = fe_zero();
   int do_scale = inverse && scale;
   if (do_scale) {
@@ -325,6 +340,10 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     scale_tw = stk_h_to_tw(c, stk_h_inv(c, nn));
   }
   bool pow2 = (n & (n - 1)) == 0;
+  if (pow2 && (wstride & (wstride - 1))) {  // the pass kernels index by shift
+    STK_TRY(stk_get_table(c, w, n, &W));
+    wstride = 1;
+  }
   if (!pow2 || n < 8) {
     if (n > 4096) return stk_fail(c, STK_EUNSUPPORTED, "non power-of-two order above 4096");
     uint64_t total = n * batch;
@@ -341,10 +360,10 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     }
     if (c->is_stark)
       dft_generic_kernel<StarkField><<<blocks, 128, 0, s>>>(src, n_in, in_stride, d_out, out_stride, n, batch, W,
-                                                           do_scale, scale_tw, StarkField());
+                                                           wstride, do_scale, scale_tw, StarkField());
     else
       dft_generic_kernel<MontField><<<blocks, 128, 0, s>>>(src, n_in, in_stride, d_out, out_stride, n, batch, W,
-                                                          do_scale, scale_tw, c->mont);
+                                                          wstride, do_scale, scale_tw, c->mont);
     STK_CUDA(c, cudaGetLastError());
     return STK_OK;
   }
@@ -362,6 +381,7 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     NttPass& P = plan[i];
     P.batch = (uint32_t)batch;
     P.W = W;
+    P.tw_shift = ilog2_u64(wstride);
     P.do_scale = (P.final_pass && do_scale) ? 1 : 0;
     P.scale = scale_tw;
     P.zbit = 32;

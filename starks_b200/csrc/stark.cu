@@ -88,21 +88,21 @@ constexpr int kScanChunk = 8;      // elements per thread
 constexpr int kScanThreads = 256;  // threads per block -> 2048 elements per block
 
 template <class F>
-__device__ __forceinline__ fe scan_load(const fe* a, const fe* rpow, uint64_t n, uint64_t i, const F& f) {
+__device__ __forceinline__ fe scan_load(const fe* a, const fe* rpow, uint64_t rs, uint64_t n, uint64_t i, const F& f) {
   if (i >= n) return fe_zero();
   fe v = fe_load(a + i);
-  return rpow ? f.mul_tw(v, fe_load_ro(rpow + i)) : v;
+  return rpow ? f.mul_tw(v, fe_load_ro(rpow + i * rs)) : v;
 }
 
 // phase 1: block totals
 template <class F>
 __global__ void __launch_bounds__(kScanThreads) scan_block_totals_kernel(const fe* __restrict__ a, const fe* __restrict__ rpow,
-                                                                         uint64_t n, fe* __restrict__ totals, const F f) {
+                                                                         uint64_t rs, uint64_t n, fe* __restrict__ totals, const F f) {
   __shared__ fe sh[kScanThreads];
   const uint64_t base = ((uint64_t)blockIdx.x * kScanThreads + threadIdx.x) * kScanChunk;
   fe s = fe_zero();
 #pragma unroll
-  for (int u = 0; u < kScanChunk; ++u) s = f.add(s, scan_load(a, rpow, n, base + u, f));
+  for (int u = 0; u < kScanChunk; ++u) s = f.add(s, scan_load(a, rpow, rs, n, base + u, f));
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int off = kScanThreads / 2; off > 0; off >>= 1) {
@@ -126,8 +126,8 @@ __global__ void scan_totals_kernel(fe* totals, uint64_t nblocks, const F f) {
 
 // phase 3: exclusive suffix sums inside each block + block offset, then unscale
 template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_finish_kernel(const fe* __restrict__ a, const fe* __restrict__ rpow,
-                                                                   const fe* __restrict__ rinvpow, uint64_t n,
+__global__ void __launch_bounds__(kScanThreads) scan_finish_kernel(const fe* __restrict__ a, const fe* __restrict__ rpow, uint64_t rs,
+                                                                   const fe* __restrict__ rinvpow, uint64_t ris, uint64_t n,
                                                                    const fe* __restrict__ totals, fe* __restrict__ out,
                                                                    const F f) {
   __shared__ fe sh[kScanThreads];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_finish_kernel(const fe* __r
   fe v[kScanChunk];
   fe s = fe_zero();
 #pragma unroll
-  for (int u = 0; u < kScanChunk; ++u) { v[u] = scan_load(a, rpow, n, base + u, f); s = f.add(s, v[u]); }
+  for (int u = 0; u < kScanChunk; ++u) { v[u] = scan_load(a, rpow, rs, n, base + u, f); s = f.add(s, v[u]); }
   sh[threadIdx.x] = s;
   __syncthreads();
   // inclusive suffix scan over thread sums (Hillis-Steele)
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_finish_kernel(const fe* __r
     const uint64_t k = base + u;
     if (k + 1 < n) {
       fe r = after;
-      if (rinvpow) r = f.mul_tw(r, fe_load_ro(rinvpow + ((k + 1) % n)));  // r^-(k+1)
+      if (rinvpow) r = f.mul_tw(r, fe_load_ro(rinvpow + ((k + 1) % n) * ris));  // r^-(k+1)
       fe_store(out + k, r);
     }
     after = f.add(after, v[u]);
@@ -176,15 +176,16 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const fe* __restrict__ col
 }
 
 template <class F>
-int div_linear_impl(stk_ctx* c, const fe* a, uint64_t n, const fe* rpow, const fe* rinvpow, fe* out, const F& f) {
+int div_linear_impl(stk_ctx* c, const fe* a, uint64_t n, const fe* rpow, uint64_t rs, const fe* rinvpow, uint64_t ris,
+                    fe* out, const F& f) {
   const uint64_t per_block = (uint64_t)kScanChunk * kScanThreads;
   const uint64_t nblocks = (n + per_block - 1) / per_block;
   void* t;
   STK_TRY(stk_scratch(c, 2, nblocks * sizeof(fe), &t));
   fe* totals = (fe*)t;
-  scan_block_totals_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, n, totals, f);
+  scan_block_totals_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rs, n, totals, f);
   scan_totals_kernel<F><<<1, 32, 0, c->stream>>>(totals, nblocks, f);
-  scan_finish_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rinvpow, n, totals, out, f);
+  scan_finish_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rs, rinvpow, ris, n, totals, out, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }
@@ -259,14 +260,15 @@ STK_API int stk_div_linear(stk_ctx* c, const uint32_t* d_a, uint64_t n, const ui
   fe one = host::reduce(host::from_u64(1), c->p);
   const fe* rpow = nullptr;
   const fe* rinvpow = nullptr;
+  uint64_t rs = 1, ris = 1;
   if (!fe_eq(rr, one)) {
     if (r_order < n) return stk_fail(c, STK_EINVAL, "order of r must be at least the coefficient count");
     if (!fe_eq(stk_h_pow(c, rr, r_order), one)) return stk_fail(c, STK_EINVAL, "r^order != 1");
-    STK_TRY(stk_get_table(c, rr, r_order, &rpow));
-    STK_TRY(stk_get_table(c, stk_h_inv(c, rr), r_order, &rinvpow));
+    STK_TRY(stk_get_table_strided(c, rr, r_order, &rpow, &rs));
+    STK_TRY(stk_get_table_strided(c, stk_h_inv(c, rr), r_order, &rinvpow, &ris));
   }
-  if (c->is_stark) return div_linear_impl<StarkField>(c, (const fe*)d_a, n, rpow, rinvpow, (fe*)d_out, StarkField());
-  return div_linear_impl<MontField>(c, (const fe*)d_a, n, rpow, rinvpow, (fe*)d_out, c->mont);
+  if (c->is_stark) return div_linear_impl<StarkField>(c, (const fe*)d_a, n, rpow, rs, rinvpow, ris, (fe*)d_out, StarkField());
+  return div_linear_impl<MontField>(c, (const fe*)d_a, n, rpow, rs, rinvpow, ris, (fe*)d_out, c->mont);
 }
 
 // out[i] = sum_c weights[c] * cols[c][i]
