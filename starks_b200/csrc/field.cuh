@@ -349,8 +349,9 @@ struct MontField {
     if (sub8(d.v, a.v, b.v)) add8(d.v, d.v, p.v);
     return d;
   }
-  // a*b/R mod p
-  __host__ __device__ __forceinline__ fe mmul(const fe& a, const fe& b) const {
+  // a*b/R mod p.  Deliberately NOT inlined on the device: the run-time-modulus path is for
+  // small test fields, and one out-of-line copy keeps the kernels' compile time in seconds.
+  __host__ __device__ __noinline__ fe mmul(const fe& a, const fe& b) const {
     uint32_t t[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) t[i] = 0;

@@ -202,10 +202,9 @@ int stk_get_table_strided(stk_ctx* c, const fe& root, uint64_t n, const fe** d_t
 
 static int ilog2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) ++l; return l; }
 
-static int ntt_max_radix() { return env_int("STK_NTT_RADIX", 3) >= 3 ? 3 : 2; }
+static int ntt_max_radix() { return 3; }  // radix-4 measured no faster: profiles/r01_ntt_radix_sweep.txt
 
-static void fill_rounds(NttPass& P) {
-  const int R = ntt_max_radix();
+static void fill_rounds(NttPass& P, int R) {
   int k = P.k, rem = k % R, idx = 0;
   if (rem) P.r[idx++] = rem;
   for (int i = 0; i < k / R; ++i) P.r[idx++] = R;
@@ -213,8 +212,8 @@ static void fill_rounds(NttPass& P) {
 }
 
 // Cuts the n index bits into passes (top bits first) and fixes each pass's tile geometry.
-static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
-  const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 10)));
+static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan, int rmax) {
+  const int logT = std::min(10, std::max(6, env_int("STK_NTT_LOGT", 10)));  // tiles of <= 1024 elements
   const int kmax = std::min(logT, std::max(3, env_int("STK_NTT_KMAX", 11)));
   plan.clear();
   if (n <= kmax) {
@@ -225,7 +224,7 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
     P.logT = P.k + P.logC;
     P.c_is_col = 1; P.cb = 0; P.nl = 0; P.sl = 0; P.sh = 0;
     P.final_pass = 1;
-    fill_rounds(P);
+    fill_rounds(P, rmax);
     plan.push_back(P);
     return STK_OK;
   }
@@ -249,52 +248,23 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan) {
       P.nl = n - P.logC - k; P.sl = k; P.sh = 0;
     }
     P.logT = P.k + P.logC;
-    fill_rounds(P);
+    fill_rounds(P, rmax);
     plan.push_back(P);
     hi -= k;
   }
   return STK_OK;
 }
 
-template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, bool ZS = false>
-static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     MAXT <= 256 ? 32 * 1024 : 200 * 1024));
-    attr_done = true;
-  }
-  const uint32_t T = 1u << P.logT;
-  unsigned threads = std::max(1u, T >> MAXR);
-  uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
-  uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
-  if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
-  dim3 grid((unsigned)tiles, (unsigned)cols);
-  size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
-  ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS><<<grid, threads, smem, s>>>(P, f);
-  STK_CUDA(c, cudaGetLastError());
-  return STK_OK;
-}
+// The pass kernels are instantiated in their own translation units (ntt_pass_*.cu) so that
+// they compile in parallel; this file only sees the host-side launchers.
+int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P);      // radix-8 rounds
+int stk_launch_pass_stark_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);   // + zero-skip levels
+int stk_launch_pass_mont(stk_ctx* c, cudaStream_t s, const NttPass& P);       // run-time modulus, radix-4
 
 template <class F>
-static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
-  if (ntt_max_radix() >= 3) {
-    if (P.logT <= 10) {  // 128-thread tiles: trade registers for resident CTAs
-      const int minb = env_int("STK_NTT_MINB", 4);
-      if (P.zbit < 32) return launch_pass_r<F, 3, 128, 4, true>(c, s, P, f);
-      if (minb >= 6) return launch_pass_r<F, 3, 128, 6>(c, s, P, f);
-      if (minb == 5) return launch_pass_r<F, 3, 128, 5>(c, s, P, f);
-      return launch_pass_r<F, 3, 128, 4>(c, s, P, f);
-    }
-    return launch_pass_r<F, 3>(c, s, P, f);
-  }
-  if (P.logT <= 10) {  // radix-4 rounds, 256-thread tiles
-    const int minb = env_int("STK_NTT_MINB", 3);
-    if (minb >= 4) return launch_pass_r<F, 2, 256, 4>(c, s, P, f);
-    if (minb == 3) return launch_pass_r<F, 2, 256, 3>(c, s, P, f);
-    return launch_pass_r<F, 2, 256, 2>(c, s, P, f);
-  }
-  return launch_pass_r<F, 2>(c, s, P, f);
+static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
+  if constexpr (F::kMontgomery) return stk_launch_pass_mont(c, s, P);
+  else return P.zbit < 32 ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
 }
 
 // direct DFT for orders that are not a power of two >= 8 (_simple_ft, starks/fft.py:287-300)
@@ -369,7 +339,7 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   }
   int logn = ilog2_u64(n);
   std::vector<NttPass> plan;
-  STK_TRY(build_plan(logn, batch, plan));
+  STK_TRY(build_plan(logn, batch, plan, c->is_stark ? ntt_max_radix() : 2));
   fe* tmp = nullptr;
   bool need_tmp = plan.size() > 1 || (const void*)d_in == (const void*)d_out;
   if (need_tmp) {
@@ -517,14 +487,14 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
   STK_TRY(stk_get_table(c, w, N, &W));
   std::vector<NttPass> plan;
   if (phase == 0) {
-    STK_TRY(build_plan(nloc, batch, plan));
+    STK_TRY(build_plan(nloc, batch, plan, c->is_stark ? ntt_max_radix() : 2));
     for (auto& P : plan) {
       P.final_pass = 0;  // keep the tile geometry, store in place
       P.n_tw = n; P.j_shift = g; P.j_or = (uint32_t)rank; P.out_shift = 0;
     }
   } else {
     // last g levels: bits [0, g) of the local index; final-pass geometry (batch bits on top)
-    const int logT = std::min(12, std::max(6, env_int("STK_NTT_LOGT", 10)));
+    const int logT = std::min(10, std::max(6, env_int("STK_NTT_LOGT", 10)));
     NttPass P;
     memset(&P, 0, sizeof P);
     P.n = nloc; P.k = g; P.lo = 0; P.final_pass = 1; P.c_is_col = 0;
@@ -532,7 +502,7 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
     P.cb = nloc - P.logC;
     P.nl = nloc - P.logC - g; P.sl = g; P.sh = 0;
     P.logT = P.k + P.logC;
-    fill_rounds(P);
+    fill_rounds(P, c->is_stark ? ntt_max_radix() : 2);
     P.n_tw = n; P.j_shift = 0; P.j_or = (uint32_t)(rank << nloc); P.out_shift = g;
     plan.push_back(P);
   }

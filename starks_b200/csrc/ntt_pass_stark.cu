@@ -1,0 +1,32 @@
+// ntt_pass_stark.cu -- one instantiation of the NTT pass kernel and its host-side launcher (split out of
+// ntt_api.cu so the heavy kernels compile in parallel).
+#include <algorithm>
+#include "ctx.h"
+#include "ntt.cuh"
+
+using namespace stk;
+
+template <class F, int MAXR, int MAXT, int MINB, bool ZS>
+static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+    attr_done = true;
+  }
+  const uint32_t T = 1u << P.logT;
+  if (P.logT > 10) return stk_fail(c, STK_EUNSUPPORTED, "tile above 1024 elements");
+  unsigned threads = std::max(1u, T >> MAXR);
+  uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
+  uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
+  if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
+  dim3 grid((unsigned)tiles, (unsigned)cols);
+  size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
+  ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS><<<grid, threads, smem, s>>>(P, f);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P) {
+  return launch_pass_r<StarkField, 3, 128, 4, false>(c, s, P, StarkField());
+}
