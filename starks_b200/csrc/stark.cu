@@ -112,12 +112,27 @@ __global__ void __launch_bounds__(kScanThreads) scan_block_totals_kernel(const f
   if (threadIdx.x == 0) totals[blockIdx.x] = sh[0];
 }
 
-// phase 2: exclusive suffix scan of the block totals (single block, sequential over <= 64K entries)
+// phase 2: exclusive suffix scan of the block totals, one CTA: each thread walks a contiguous
+// chunk, a Hillis-Steele suffix scan combines the chunk sums, then the chunk is rewritten.
 template <class F>
-__global__ void scan_totals_kernel(fe* totals, uint64_t nblocks, const F f) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  fe run = fe_zero();
-  for (uint64_t b = nblocks; b-- > 0;) {
+__global__ void __launch_bounds__(kScanThreads) scan_totals_kernel(fe* totals, uint64_t nblocks, const F f) {
+  __shared__ fe sh[kScanThreads];
+  const uint64_t per = (nblocks + kScanThreads - 1) / kScanThreads;
+  const uint64_t lo = threadIdx.x * per, hi = (lo + per < nblocks) ? lo + per : nblocks;
+  fe s = fe_zero();
+  for (uint64_t b = lo; b < hi; ++b) s = f.add(s, totals[b]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < kScanThreads; off <<= 1) {
+    fe t = fe_zero();
+    bool has = threadIdx.x + off < kScanThreads;
+    if (has) t = sh[threadIdx.x + off];
+    __syncthreads();
+    if (has) sh[threadIdx.x] = f.add(sh[threadIdx.x], t);
+    __syncthreads();
+  }
+  fe run = (threadIdx.x + 1 < kScanThreads) ? sh[threadIdx.x + 1] : fe_zero();  // all chunks after mine
+  for (uint64_t b = hi; b-- > lo;) {
     fe t = totals[b];
     totals[b] = run;  // sum of all blocks after b
     run = f.add(run, t);
@@ -184,7 +199,7 @@ int div_linear_impl(stk_ctx* c, const fe* a, uint64_t n, const fe* rpow, uint64_
   STK_TRY(stk_scratch(c, 2, nblocks * sizeof(fe), &t));
   fe* totals = (fe*)t;
   scan_block_totals_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rs, n, totals, f);
-  scan_totals_kernel<F><<<1, 32, 0, c->stream>>>(totals, nblocks, f);
+  scan_totals_kernel<F><<<1, kScanThreads, 0, c->stream>>>(totals, nblocks, f);
   scan_finish_kernel<F><<<(unsigned)nblocks, kScanThreads, 0, c->stream>>>(a, rpow, rs, rinvpow, ris, n, totals, out, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
