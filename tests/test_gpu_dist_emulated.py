@@ -1,0 +1,96 @@
+"""The multi-GPU kernels under the single-GPU `-m gpu` run: G ranks are emulated one after
+another on cuda:0 (no kernel waits on another), the all-to-all is a host-side regrouping of
+the ranks' buffers.  Checks stk_ntt_dist_phase (four-step NTT) and the sharded Merkle commit
+geometry against the single-GPU transform / tree.  The NCCL path itself is exercised by
+tests/gpu_dist_check.py under torchrun (profiles/r01_dist_*gpu.txt) and the index logic by
+tests/test_dist_gloo.py on CPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 2**256 - 351 * 2**32 + 1
+
+
+@pytest.fixture(scope="module")
+def eng():
+  from starks_b200 import Engine
+  e = Engine(0)
+  yield e
+  e.close()
+
+
+def rand(n, seed):
+  rng = np.random.default_rng(seed)
+  a = rng.integers(0, 2**32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+  a[:, 7] &= 0x7FFFFFFF
+  return a
+
+
+@pytest.mark.parametrize("world,logn", [(2, 6), (2, 13), (4, 14), (8, 12), (8, 21), (4, 22)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_four_step_emulated(eng, world, logn, inverse):
+  n = 1 << logn
+  L = n // world
+  g = world.bit_length() - 1
+  w = pow(7, (P - 1) // n, P)
+  x = rand(n, logn * 10 + world)
+  ref = eng.ntt_host(x.reshape(1, n, 8), n, w, inverse=inverse)[0]
+  d_a, d_b = eng.alloc(L * 32), eng.alloc(L * 32)
+  # phase 0 on every rank's cyclic shard
+  y = []
+  for r in range(world):
+    d_a.upload(np.ascontiguousarray(x[r::world]))
+    eng.ntt_dist_phase(0, d_a.ptr, d_a.ptr, L, 1, L, w, world, r, inverse)
+    y.append(d_a.download((L, 8)))
+  # all-to-all of contiguous chunks + local [r][m] -> [m][r] transpose
+  chunk = L // world
+  out = np.empty((n, 8), dtype=np.uint32)
+  for rp in range(world):
+    recv = np.stack([y[r][rp * chunk:(rp + 1) * chunk] for r in range(world)])      # [r][m_local]
+    z = np.ascontiguousarray(recv.transpose(1, 0, 2)).reshape(L, 8)                   # [m_local][r]
+    d_a.upload(z)
+    eng.ntt_dist_phase(1, d_a.ptr, d_b.ptr, L, 1, L, w, world, rp, inverse)
+    res = d_b.download((L, 8))
+    rho = int(format(rp, "0%db" % g)[::-1], 2)
+    out[rho::world] = res                                                             # X[K], K mod G = bitrev(r')
+  assert (out == ref).all()
+  d_a.free()
+  d_b.free()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_commit_emulated(eng, world):
+  """Each emulated rank commits the rows pack_rows_for_leaf_owners gives it; its nodes must be
+  the global tree's subtree G + r and the combined top levels must give the global root."""
+  import torch
+  from starks_b200.dist import pack_rows_for_leaf_owners, combine_subtree_roots
+  n, ncols = 1 << 12, 8
+  rng = np.random.default_rng(world)
+  cols = rng.integers(0, 2**32, size=(ncols, n, 8), dtype=np.uint64).astype(np.uint32)
+  cols[:, :, 7] &= 0x7FFFFFFF
+  d = eng.alloc(cols.nbytes).upload(cols)
+  nodes = eng.alloc(32 * n)
+  root = eng.merkle_commit(d.ptr, n, ncols, n, nodes.ptr)
+  full = nodes.download((n, 32), np.uint8)
+  cl = ncols // world
+  packed = [pack_rows_for_leaf_owners(torch.from_numpy(cols[s * cl:(s + 1) * cl].view(np.int32).copy()), world)
+            for s in range(world)]
+  roots = []
+  n_local = n // world
+  for r in range(world):
+    rows = torch.cat([packed[s][r] for s in range(world)], dim=0).numpy().view(np.uint32)   # (ncols, n/G, 8)
+    dr = eng.alloc(rows.nbytes).upload(np.ascontiguousarray(rows))
+    ln = eng.alloc(32 * n_local)
+    roots.append(eng.merkle_commit(dr.ptr, n_local, ncols, n_local, ln.ptr))
+    loc = ln.download((n_local, 32), np.uint8)
+    for i in (1, 2, 3, n_local // 2, n_local - 1):
+      dd = i.bit_length() - 1
+      gi = (world + r) * (1 << dd) + (i - (1 << dd))
+      assert (loc[i] == full[gi]).all()
+    dr.free()
+    ln.free()
+  top = combine_subtree_roots(roots)
+  assert top[1] == root
+  for i in range(1, 2 * world):
+    assert top[i] == full[i].tobytes()
