@@ -10,7 +10,7 @@ from .modp import element_to_int
 blake = lambda x: blake2s(x).digest()  # starks/merkle_tree.py:5
 
 
-def multiplicative_order(root: int, p: int, cap: int = 1 << 30) -> int:
+def multiplicative_order(root: int, p: int, cap: int = 1 << 16) -> int:
   """Order of root in (Z/p)*: the reference finds it by walking the power cycle
   (starks/fft.py:319-321).  Power-of-two orders are found by repeated squaring; anything else
   falls back to the walk (tiny orders only, e.g. 6 in starks/test/test_fft.py:98-113)."""
@@ -27,7 +27,7 @@ def multiplicative_order(root: int, p: int, cap: int = 1 << 30) -> int:
     x = x * root % p
     n += 1
     if n > cap:
-      raise ValueError("order of the root exceeds %d" % cap)
+      raise ValueError("the root's order is neither a power of two nor <= %d" % cap)
   return n
 
 
