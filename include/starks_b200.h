@@ -95,6 +95,13 @@ int stk_power_cycle(stk_ctx* ctx, const uint32_t r[8], uint64_t n, uint32_t* d_o
 int stk_ntt_dist_phase(stk_ctx* ctx, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n,
                        uint64_t batch, uint64_t stride, const uint32_t root[8], uint64_t nranks, uint64_t rank,
                        int inverse);
+/* Phase 0 FUSED with the exchange: the last pass of phase 0 stores each element straight into
+ * the owning rank's buffer through peer pointers (peer_ptrs[r] = rank r's exchange buffer
+ * mapped into this process; NVLink P2P stores, 256-byte runs), laid out [source rank][m].
+ * After a cross-rank barrier, stk_ntt_dist_phase(phase = 2, ...) runs phase 1 directly on
+ * that layout: no all-to-all and no transpose pass. */
+int stk_ntt_dist_phase0_p2p(stk_ctx* ctx, uint32_t* d_inout, uint64_t local_n, const uint32_t root[8],
+                            uint64_t nranks, uint64_t rank, int inverse, const uint64_t* peer_ptrs);
 
 /* ---- LDE ------------------------------------------------------------------------ */
 /* construct_trace_polynomials + evaluation loop (starks/stark.py:27-36, 254-256): per column

@@ -51,6 +51,15 @@ struct NttPass {
   int j_shift;
   uint32_t j_or;
   int out_shift;
+  // fused transpose of the four-step transform: a non-final pass with peer_on stores element
+  // K not locally but into rank (K >> peer_log_chunk)'s buffer, at [this rank][K mod chunk]
+  // (P2P stores over NVLink, contiguous 256-byte runs per thread); in_rot makes the next
+  // phase read that [source rank][m] layout as if it were [m][source rank].
+  int peer_on;
+  int peer_log_chunk;
+  uint32_t peer_self;
+  int in_rot;
+  fe* peer_out[8];
   const fe* in;
   fe* out;
   const fe* W;
@@ -85,7 +94,8 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         uint32_t J = J0 + ((uint32_t)m << gshift);
-        x[m] = (col_ok && J < A.n_in) ? fe_load(src + J) : fe_zero();
+        uint32_t Jm = A.in_rot ? (((J & ((1u << A.in_rot) - 1u)) << (A.n - A.in_rot)) | (J >> A.in_rot)) : J;
+        x[m] = (col_ok && J < A.n_in) ? fe_load(src + Jm) : fe_zero();
       }
     } else {
 #pragma unroll
@@ -133,7 +143,12 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
           uint32_t K = A.final_pass ? ((__brev((J << A.j_shift) | A.j_or) >> (32 - A.n_tw)) >> A.out_shift) : J;
           fe v = x[m];
           if (A.do_scale) v = f.mul_tw(v, A.scale);
-          fe_store(dst + K, v);
+          if (A.peer_on) {
+            fe* pd = A.peer_out[K >> A.peer_log_chunk];
+            fe_store(pd + ((A.peer_self << A.peer_log_chunk) | (K & ((1u << A.peer_log_chunk) - 1u))), v);
+          } else {
+            fe_store(dst + K, v);
+          }
         }
       }
     } else {

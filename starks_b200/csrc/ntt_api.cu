@@ -466,9 +466,9 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_host(stk_ctx* c, c
 //   phase 1: the last g = log2(G) levels and the bit-reversed store; the output index K has
 //           K mod G = bitrev_g(r'), and rank r' keeps X[K] at local position K >> g
 //           (cyclic output, k2-sharded as in App. C.4).
-extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
-    stk_ctx* c, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n, uint64_t batch, uint64_t stride,
-    const uint32_t root[8], uint64_t nranks, uint64_t rank, int inverse) {
+static int dist_phase_impl(stk_ctx* c, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n, uint64_t batch,
+                           uint64_t stride, const uint32_t root[8], uint64_t nranks, uint64_t rank, int inverse,
+                           const uint64_t* peer_ptrs, int rotated_input) {
   if (!c || !d_in || !d_out || !root || local_n == 0 || batch == 0) return STK_EINVAL;
   if ((local_n & (local_n - 1)) || (nranks & (nranks - 1)) || nranks < 2 || rank >= nranks || nranks > 8)
     return stk_fail(c, STK_EINVAL, "local length and rank count must be powers of two (2..8 ranks)");
@@ -492,6 +492,12 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
       P.final_pass = 0;  // keep the tile geometry, store in place
       P.n_tw = n; P.j_shift = g; P.j_or = (uint32_t)rank; P.out_shift = 0;
     }
+    if (peer_ptrs) {  // the last pass scatters straight into the peers' exchange buffers
+      if (batch != 1) return stk_fail(c, STK_EUNSUPPORTED, "peer scatter handles one column");
+      NttPass& L = plan.back();
+      L.peer_on = 1; L.peer_log_chunk = nloc - g; L.peer_self = (uint32_t)rank;
+      for (uint64_t r2 = 0; r2 < nranks; ++r2) L.peer_out[r2] = (fe*)(uintptr_t)peer_ptrs[r2];
+    }
   } else {
     // last g levels: bits [0, g) of the local index; final-pass geometry (batch bits on top)
     const int logT = std::min(10, std::max(6, env_int("STK_NTT_LOGT", 10)));
@@ -504,6 +510,7 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
     P.logT = P.k + P.logC;
     fill_rounds(P, c->is_stark ? ntt_max_radix() : 2);
     P.n_tw = n; P.j_shift = 0; P.j_or = (uint32_t)(rank << nloc); P.out_shift = g;
+    P.in_rot = rotated_input ? g : 0;
     plan.push_back(P);
   }
   fe scale_tw = fe_zero();
@@ -525,6 +532,25 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
     else STK_TRY(launch_pass<MontField>(c, c->stream, P, c->mont));
   }
   return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase(
+    stk_ctx* c, int phase, const uint32_t* d_in, uint32_t* d_out, uint64_t local_n, uint64_t batch, uint64_t stride,
+    const uint32_t root[8], uint64_t nranks, uint64_t rank, int inverse) {
+  if (phase == 2)  // phase 1 on the untransposed exchange layout [source rank][m]
+    return dist_phase_impl(c, 1, d_in, d_out, local_n, batch, stride, root, nranks, rank, inverse, nullptr, 1);
+  return dist_phase_impl(c, phase, d_in, d_out, local_n, batch, stride, root, nranks, rank, inverse, nullptr, 0);
+}
+
+// Phase 0 fused with the transpose: the last pass stores every element directly into the
+// owning rank's exchange buffer over NVLink (peer_ptrs[r] = rank r's buffer mapped into this
+// process, e.g. torch symmetric memory), so no separate all-to-all or transpose pass runs.
+// The caller orders it with a cross-rank barrier before stk_ntt_dist_phase(phase = 2).
+extern "C" __attribute__((visibility("default"))) int stk_ntt_dist_phase0_p2p(
+    stk_ctx* c, uint32_t* d_inout, uint64_t local_n, const uint32_t root[8], uint64_t nranks, uint64_t rank,
+    int inverse, const uint64_t* peer_ptrs) {
+  if (!peer_ptrs) return STK_EINVAL;
+  return dist_phase_impl(c, 0, d_inout, d_inout, local_n, 1, local_n, root, nranks, rank, inverse, peer_ptrs, 0);
 }
 
 // ------------------------------------------------------------------ pointwise helpers

@@ -164,3 +164,30 @@ def dist_ntt(engine, x_cyclic: torch.Tensor, root: int, inverse=False, group=Non
   out = torch.empty_like(z)
   engine.ntt_dist_phase(1, z.data_ptr(), out.data_ptr(), L, 1, L, root, world, rank, inverse)
   return out
+
+
+class FourStepP2P(object):
+  """dist_ntt with the exchange fused into the compute kernel: the last pass of phase 0 stores
+  its results directly into the destination ranks' exchange buffers over NVLink (peer
+  pointers from torch symmetric memory), so neither an NCCL all-to-all nor a transpose pass
+  runs; two device-side barriers order the exchange.  One column of L = N/G elements per rank."""
+
+  def __init__(self, engine, local_n: int, device, group=None):
+    import torch.distributed._symmetric_memory as symm_mem
+    self.eng, self.L = engine, local_n
+    self.group = group if group is not None else dist.group.WORLD
+    self.world, self.rank = _world(group)
+    self.recv = symm_mem.empty((local_n, 8), dtype=torch.int32, device=device)
+    self.hdl = symm_mem.rendezvous(self.recv, self.group)
+    self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+  def ntt(self, x_cyclic: torch.Tensor, root: int, inverse=False) -> torch.Tensor:
+    _adopt_stream(self.eng, x_cyclic)
+    y = x_cyclic.clone()
+    self.hdl.barrier(channel=0)          # every rank is done reading its exchange buffer
+    self.eng.ntt_dist_phase0_p2p(y.data_ptr(), self.L, root, self.world, self.rank, self.ptrs, inverse)
+    self.hdl.barrier(channel=1)          # every rank's stores have landed
+    out = torch.empty_like(x_cyclic)
+    self.eng.ntt_dist_phase(2, self.recv.data_ptr(), out.data_ptr(), self.L, 1, self.L, root, self.world, self.rank,
+                            inverse)
+    return out

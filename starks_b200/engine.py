@@ -163,6 +163,12 @@ class Engine:
                                             _u32(int_to_limbs(int(root) % self.p)), nranks, rank,
                                             int(bool(inverse))))
 
+  def ntt_dist_phase0_p2p(self, d_inout, local_n, root, nranks, rank, peer_ptrs, inverse=False):
+    """Phase 0 with the exchange fused into its last pass (stk_ntt_dist_phase0_p2p)."""
+    arr = (ctypes.c_uint64 * nranks)(*[int(p) for p in peer_ptrs])
+    self._check(self.lib.stk_ntt_dist_phase0_p2p(self.ctx, d_inout, local_n, _u32(int_to_limbs(int(root) % self.p)),
+                                                 nranks, rank, int(bool(inverse)), arr))
+
   def mul_polys(self, a, b, n, root):
     a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 8)
     b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 8)

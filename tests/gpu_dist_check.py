@@ -55,6 +55,43 @@ for logn in (8, 12, 16, 20, 22):
   res["dist_ntt_2^%d_ok" % logn] = bool(ok)
   assert ok, "dist_ntt mismatch at 2^%d on rank %d" % (logn, rank)
 
+# ---------------- parity + timing: fused exchange (P2P stores from the phase-0 kernel)
+try:
+  for logn in (12, 20, 26):
+    n = 1 << logn
+    L = n // world
+    w = pow(7, (P - 1) // n, P)
+    fs = sd.FourStepP2P(eng, L, dev)
+    if logn < 26:
+      x = rand_limbs((n,), 300 + logn).to(dev)
+      ref = torch.empty_like(x)
+      sd._adopt_stream(eng, x)
+      eng.ntt(x.data_ptr(), n, n, ref.data_ptr(), n, n, 1, w)
+      mine = x[rank::world].contiguous()
+      out = fs.ntt(mine, w)
+      torch.cuda.synchronize()
+      g = world.bit_length() - 1
+      rho = int(format(rank, "0%db" % g)[::-1], 2) if g else 0
+      ok = torch.equal(out, ref[rho::world])
+      res["p2p_ntt_2^%d_ok" % logn] = bool(ok)
+      assert ok, "fused-exchange NTT mismatch at 2^%d on rank %d" % (logn, rank)
+    else:
+      mine = torch.randint(0, 2**31 - 1, (L, 8), dtype=torch.int32, device=dev)
+      for _ in range(2):
+        fs.ntt(mine, w)
+      torch.cuda.synchronize(); dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(3):
+        fs.ntt(mine, w)
+      e1.record()
+      torch.cuda.synchronize()
+      res["cfg4_p2p_ntt_2^26_ms"] = tmax(e0.elapsed_time(e1) / 3)
+    del fs
+except Exception as ex:
+  import traceback
+  res["p2p_error"] = traceback.format_exc()[-600:]
+
 # ---------------- parity: sharded LDE + commit
 steps, ext, ncols = 1 << 12, 8, 8
 n = steps * ext

@@ -94,3 +94,28 @@ def test_sharded_commit_emulated(eng, world):
   assert top[1] == root
   for i in range(1, 2 * world):
     assert top[i] == full[i].tobytes()
+
+
+@pytest.mark.parametrize("world,logn", [(2, 9), (4, 14), (8, 16), (8, 21)])
+def test_four_step_fused_exchange_emulated(eng, world, logn):
+  """stk_ntt_dist_phase0_p2p: the last pass of phase 0 scatters into the ranks' exchange
+  buffers (here G buffers on one GPU stand in for the peers), phase 2 reads that layout."""
+  n = 1 << logn
+  L = n // world
+  g = world.bit_length() - 1
+  w = pow(7, (P - 1) // n, P)
+  x = rand(n, 77 + logn)
+  ref = eng.ntt_host(x.reshape(1, n, 8), n, w)[0]
+  recv = [eng.alloc(L * 32) for _ in range(world)]
+  work, outb = eng.alloc(L * 32), eng.alloc(L * 32)
+  for r in range(world):
+    work.upload(np.ascontiguousarray(x[r::world]))
+    eng.ntt_dist_phase0_p2p(work.ptr, L, w, world, r, [b.ptr for b in recv])
+  out = np.empty((n, 8), dtype=np.uint32)
+  for rp in range(world):
+    eng.ntt_dist_phase(2, recv[rp].ptr, outb.ptr, L, 1, L, w, world, rp)
+    rho = int(format(rp, "0%db" % g)[::-1], 2)
+    out[rho::world] = outb.download((L, 8))
+  assert (out == ref).all()
+  for b in recv + [work, outb]:
+    b.free()
