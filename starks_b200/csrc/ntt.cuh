@@ -134,7 +134,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
         }
       }
     }
-    if (last) {
+    if (last && !A.peer_on) {
       if (col_ok) {
         fe* dst = A.out + (unsigned long long)col * A.out_col_stride;
 #pragma unroll
@@ -143,12 +143,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
           uint32_t K = A.final_pass ? ((__brev((J << A.j_shift) | A.j_or) >> (32 - A.n_tw)) >> A.out_shift) : J;
           fe v = x[m];
           if (A.do_scale) v = f.mul_tw(v, A.scale);
-          if (A.peer_on) {
-            fe* pd = A.peer_out[K >> A.peer_log_chunk];
-            fe_store(pd + ((A.peer_self << A.peer_log_chunk) | (K & ((1u << A.peer_log_chunk) - 1u))), v);
-          } else {
-            fe_store(dst + K, v);
-          }
+          fe_store(dst + K, v);
         }
       }
     } else {
@@ -178,6 +173,23 @@ __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, c
     else if (r == 2) ntt_round<F, 2, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
     else ntt_round<F, 1, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
     if (!last) __syncthreads();
+  }
+  if (A.peer_on) {
+    // Fused exchange: the finished tile sits in shared memory; write it to the owning ranks'
+    // buffers with consecutive lanes on consecutive 16-byte chunks, so every warp store is a
+    // contiguous 512-byte run over NVLink (a direct per-thread store would issue 16/32-byte
+    // fragments 256 bytes apart and reach a quarter of the link rate).
+    __syncthreads();
+    const uint4* s4 = reinterpret_cast<const uint4*>(sm);
+    const uint32_t Lm = (1u << A.k) - 1u, cmask = (1u << A.peer_log_chunk) - 1u;
+    for (uint32_t q = threadIdx.x; q < 2u * T; q += blockDim.x) {
+      const uint32_t e = q >> 1, h = q & 1u;
+      const uint32_t c = e >> A.k, j = e & Lm;
+      const uint32_t J = Jcta | (j << A.lo) | (A.c_is_col ? 0u : (c << A.cb));
+      const uint4 v = s4[h * T + sm_phys((j << A.logC) | c)];
+      fe* pd = A.peer_out[J >> A.peer_log_chunk];
+      reinterpret_cast<uint4*>(pd + ((A.peer_self << A.peer_log_chunk) | (J & cmask)))[h] = v;
+    }
   }
 }
 

@@ -21,7 +21,7 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
   if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
   dim3 grid((unsigned)tiles, (unsigned)cols);
-  size_t smem = P.nrounds > 1 ? (size_t)32 * T : 0;
+  size_t smem = (P.nrounds > 1 || P.peer_on) ? (size_t)32 * T : 0;
   ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS><<<grid, threads, smem, s>>>(P, f);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
