@@ -115,6 +115,14 @@ int stk_lde_commit(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64
                    uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride, uint8_t* d_nodes,
                    uint8_t* h_root);
 
+/* stk_lde for a column shard with the commit's exchange fused in: the final pass of the forward
+ * transform stores every evaluation row straight into the rank that owns the row's leaf range
+ * (peer_ptrs[r] = rank r's (cols_total x N/nranks) row buffer mapped into this process; rows
+ * arrive in the order of a local tree under permute4, merkle_tree.py:11-23).  After a
+ * cross-rank barrier each rank runs stk_merkle_commit on its buffer (global node nranks + r). */
+int stk_lde_p2p(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                uint64_t cols, const uint32_t g2[8], uint64_t nranks, uint64_t col_base, const uint64_t* peer_ptrs);
+
 /* ---- Merkle ---------------------------------------------------------------------- */
 /* merkelize_polynomial_evaluations + merkelize (starks/merkle_tree.py:36-56, 94-119) over
  * `ncols` device columns of n rows (n a power of two >= 4): leaf(row) = concatenation of the

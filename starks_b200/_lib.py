@@ -49,6 +49,7 @@ SIGNATURES = {
     "stk_ntt_dist_phase": (cint, [vp, cint, vp, vp, u64, u64, u64, u32p, u64, u64, cint]),
     "stk_ntt_dist_phase0_p2p": (cint, [vp, vp, u64, u32p, u64, u64, cint, u64p]),
     "stk_lde": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, u64]),
+    "stk_lde_p2p": (cint, [vp, vp, u64, u64, u64, u64, u32p, u64, u64, u64p]),
     "stk_lde_commit": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, vp]),
     "stk_merkle_commit": (cint, [vp, vp, u64, u64, u64, vp, vp]),
     "stk_merkle_commit_raw": (cint, [vp, vp, u64, u64, vp, vp]),

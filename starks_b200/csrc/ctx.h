@@ -64,6 +64,14 @@ int stk_get_table(stk_ctx* c, const stk::fe& root, uint64_t n, const stk::fe** d
 // reuse the big table instead of building and caching their own.
 int stk_get_table_strided(stk_ctx* c, const stk::fe& root, uint64_t n, const stk::fe** d_table, uint64_t* stride);
 stk::fe stk_load_fe(const uint32_t* w);
+// optional peer scatter of a transform's final pass (sharded commit, see ntt.cuh peer_on = 2)
+struct stk_peer_leaf {
+  int g;                      // log2 of the rank count
+  uint32_t col0;              // global index of this rank's first column
+  const uint64_t* ptrs;       // nranks exchange buffers (columns_total x N/G elements each)
+};
+int stk_ntt_dev_peer(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, uint64_t n, uint64_t batch,
+                     const stk::fe& root, const stk_peer_leaf& peer);
 int stk_ntt_dev(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, stk::fe* d_out,
                 uint64_t out_stride, uint64_t n, uint64_t batch, const stk::fe& root, int inverse, int scale);
 // field-generic host helpers

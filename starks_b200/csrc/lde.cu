@@ -39,3 +39,28 @@ STK_API int stk_lde_commit(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, 
   STK_TRY(stk_lde(c, d_trace, steps, trace_stride, ext, cols, g2, nullptr, 0, d_evals, eval_stride));
   return stk_merkle_commit(c, d_evals, steps * ext, cols, eval_stride, d_nodes, h_root);
 }
+
+// stk_lde whose final NTT pass stores every evaluation row directly into the rank that owns
+// the row's Merkle leaf (P2P stores over NVLink; see ntt.cuh, peer_on = 2): the column-sharded
+// LDE and the column->leaf-range exchange of the sharded commit in one kernel.  peer_ptrs[r] is
+// rank r's (cols_total x N/nranks) row buffer mapped into this process.
+STK_API int stk_lde_p2p(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                        uint64_t cols, const uint32_t g2[8], uint64_t nranks, uint64_t col_base,
+                        const uint64_t* peer_ptrs) {
+  if (!c || !d_trace || !g2 || !peer_ptrs || steps == 0 || ext == 0 || cols == 0) return STK_EINVAL;
+  if (nranks < 2 || nranks > 8 || (nranks & (nranks - 1))) return stk_fail(c, STK_EINVAL, "2, 4 or 8 ranks");
+  const uint64_t n = steps * ext;
+  if (n & (n - 1)) return stk_fail(c, STK_EINVAL, "steps*ext must be a power of two");
+  fe G2 = stk_load_fe(g2);
+  fe G1 = stk_h_pow(c, G2, ext);
+  void* t;
+  STK_TRY(stk_scratch(c, 1, cols * steps * sizeof(fe), &t));
+  fe* coef = (fe*)t;
+  STK_TRY(stk_ntt_dev(c, (const fe*)d_trace, steps, trace_stride, coef, steps, steps, cols, G1, 1, 1));
+  stk_peer_leaf peer;
+  peer.g = 0;
+  while ((1ull << peer.g) < nranks) ++peer.g;
+  peer.col0 = (uint32_t)col_base;
+  peer.ptrs = peer_ptrs;
+  return stk_ntt_dev_peer(c, coef, steps, steps, n, cols, G2, peer);
+}

@@ -55,9 +55,15 @@ struct NttPass {
   // K not locally but into rank (K >> peer_log_chunk)'s buffer, at [this rank][K mod chunk]
   // (P2P stores over NVLink, contiguous 256-byte runs per thread); in_rot makes the next
   // phase read that [source rank][m] layout as if it were [m][source rank].
+  // peer_on = 2 (sharded Merkle commit): the FINAL pass stores output row K of column
+  // peer_col0 + col into the rank that owns K's leaf range under permute4
+  // (starks/merkle_tree.py:11-23): with q = N/4, K = j4*q + d*(q/G) + i goes to rank d, local
+  // row j4*(q/G) + i of a (columns x N/G) buffer -- the rows of a local tree in permute4 order.
   int peer_on;
   int peer_log_chunk;
   uint32_t peer_self;
+  int peer_g;
+  uint32_t peer_col0;
   int in_rot;
   fe* peer_out[8];
   const fe* in;
@@ -174,7 +180,27 @@ __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, c
     else ntt_round<F, 1, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
     if (!last) __syncthreads();
   }
-  if (A.peer_on) {
+  if (A.peer_on == 2) {
+    // Fused leaf exchange of the sharded commit: rows leave for their leaf owners, consecutive
+    // lanes on consecutive 16-byte chunks of consecutive output rows (runs of C rows).
+    __syncthreads();
+    const uint4* s4 = reinterpret_cast<const uint4*>(sm);
+    const uint32_t Cm = (1u << A.logC) - 1u;
+    const int qb = A.n - 2 - A.peer_g;  // log2 of rows per (quarter, owner)
+    for (uint32_t q = threadIdx.x; q < 2u * T; q += blockDim.x) {
+      const uint32_t e = q >> 1, h = q & 1u;
+      const uint32_t jr = e >> A.logC, cr = e & Cm;
+      const uint32_t c = A.logC ? (__brev(cr) >> (32 - A.logC)) : 0u;
+      const uint32_t j = __brev(jr) >> (32 - A.k);
+      const uint32_t J = Jcta | (j << A.lo) | (c << A.cb);
+      const uint32_t K = __brev(J) >> (32 - A.n);
+      const uint32_t j4 = K >> (A.n - 2), rem = K & ((1u << (A.n - 2)) - 1u);
+      const uint32_t d = rem >> qb, i = rem & ((1u << qb) - 1u);
+      const unsigned long long off =
+          ((unsigned long long)(A.peer_col0 + col0) << (A.n - A.peer_g)) + ((j4 << qb) | i);
+      reinterpret_cast<uint4*>(A.peer_out[d] + off)[h] = s4[h * T + sm_phys((j << A.logC) | c)];
+    }
+  } else if (A.peer_on) {
     // Fused exchange: the finished tile sits in shared memory; write it to the owning ranks'
     // buffers with consecutive lanes on consecutive 16-byte chunks, so every warp store is a
     // contiguous 512-byte run over NVLink (a direct per-thread store would issue 16/32-byte

@@ -287,7 +287,7 @@ __global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stri
 
 static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_in, uint64_t n_in, uint64_t in_stride,
                       fe* d_out, uint64_t out_stride, uint64_t n, uint64_t batch, const fe& root, int inverse,
-                      int scale) {
+                      int scale, const stk_peer_leaf* peer = nullptr) {
   if (n == 0 || batch == 0) return STK_OK;
   if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
                                 (unsigned long long)n_in, (unsigned long long)n);
@@ -341,6 +341,8 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   std::vector<NttPass> plan;
   STK_TRY(build_plan(logn, batch, plan, c->is_stark ? ntt_max_radix() : 2));
   fe* tmp = nullptr;
+  if (peer && (plan.size() < 2 || logn - 2 - peer->g < plan.back().logC))
+    return stk_fail(c, STK_EUNSUPPORTED, "peer scatter needs a multi-pass transform (N >= 2^11) and N/4G >= tile width");
   bool need_tmp = plan.size() > 1 || (const void*)d_in == (const void*)d_out;
   if (need_tmp) {
     void* t;
@@ -379,11 +381,21 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     } else {
       P.in = tmp; P.in_col_stride = n; P.n_in = (uint32_t)n;
       P.out = d_out; P.out_col_stride = out_stride;
+      if (peer) {
+        P.peer_on = 2; P.peer_g = peer->g; P.peer_col0 = peer->col0;
+        for (int r2 = 0; r2 < (1 << peer->g); ++r2) P.peer_out[r2] = (fe*)(uintptr_t)peer->ptrs[r2];
+      }
     }
     if (c->is_stark) STK_TRY(launch_pass<StarkField>(c, s, P, StarkField()));
     else STK_TRY(launch_pass<MontField>(c, s, P, c->mont));
   }
   return STK_OK;
+}
+
+int stk_ntt_dev_peer(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, uint64_t n, uint64_t batch,
+                     const fe& root, const stk_peer_leaf& peer) {
+  // d_out is never written in peer mode; any distinct non-null pointer keeps the in-place logic off
+  return ntt_dev_on(c, c->stream, 0, d_in, n_in, in_stride, (fe*)(uintptr_t)16, n, n, batch, root, 0, 0, &peer);
 }
 
 int stk_ntt_dev(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, fe* d_out, uint64_t out_stride,

@@ -191,3 +191,35 @@ class FourStepP2P(object):
     self.eng.ntt_dist_phase(2, self.recv.data_ptr(), out.data_ptr(), self.L, 1, self.L, root, self.world, self.rank,
                             inverse)
     return out
+
+
+class ShardedCommitP2P(object):
+  """ShardedCommit with the exchange fused into the LDE: the final pass of every rank's forward
+  transform stores each evaluation row directly into the leaf owner's row buffer over NVLink
+  (stk_lde_p2p), so the column-sharded evaluations never exist and no all-to-all runs."""
+
+  def __init__(self, engine, cols_total: int, n: int, device, group=None):
+    import torch.distributed._symmetric_memory as symm_mem
+    self.eng, self.n, self.cols_total = engine, n, cols_total
+    self.group = group if group is not None else dist.group.WORLD
+    self.world, self.rank = _world(group)
+    self.n_local = n // self.world
+    self.rows = symm_mem.empty((cols_total, self.n_local, 8), dtype=torch.int32, device=device)
+    self.hdl = symm_mem.rendezvous(self.rows, self.group)
+    self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+    self.nodes = torch.empty((self.n_local, 32), dtype=torch.uint8, device=device)
+
+  def lde_commit(self, trace: torch.Tensor, ext: int, g2: int):
+    """trace: (cols_local, steps, 8) int32 CUDA tensor.  Returns (root, top_nodes); the rows of
+    this rank's leaf range (all columns) stay in self.rows, its subtree nodes in self.nodes."""
+    cl, steps, _ = trace.shape
+    assert steps * ext == self.n and cl * self.world == self.cols_total
+    _adopt_stream(self.eng, trace)
+    self.hdl.barrier(channel=0)          # nobody still reads the previous commit's rows
+    self.eng.lde_p2p(trace.data_ptr(), steps, steps, ext, cl, g2, self.world, self.rank * cl, self.ptrs)
+    self.hdl.barrier(channel=1)          # all rows have landed
+    sub_root = self.eng.merkle_commit(self.rows.data_ptr(), self.n_local, self.cols_total, self.n_local,
+                                      self.nodes.data_ptr())
+    roots = allgather_roots(sub_root, self.group, device=trace.device)
+    top = combine_subtree_roots(roots)
+    return top[1], top

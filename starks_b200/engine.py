@@ -195,6 +195,12 @@ class Engine:
                                  _u32(int_to_limbs(int(g2) % self.p)), d_coeffs or None, coeff_stride, d_evals,
                                  eval_stride))
 
+  def lde_p2p(self, d_trace, steps, trace_stride, ext, cols, g2, nranks, col_base, peer_ptrs):
+    """LDE of a column shard whose final pass scatters rows to their leaf owners (stk_lde_p2p)."""
+    arr = (ctypes.c_uint64 * nranks)(*[int(p) for p in peer_ptrs])
+    self._check(self.lib.stk_lde_p2p(self.ctx, d_trace, steps, trace_stride, ext, cols,
+                                     _u32(int_to_limbs(int(g2) % self.p)), nranks, col_base, arr))
+
   def lde_commit(self, d_trace, steps, trace_stride, ext, cols, g2, d_evals, eval_stride, d_nodes):
     root = (ctypes.c_uint8 * 32)()
     self._check(self.lib.stk_lde_commit(self.ctx, d_trace, steps, trace_stride, ext, cols,

@@ -131,6 +131,38 @@ res["cfg3_lde_merkle_commit_ms"] = tmax((time.perf_counter() - t0) / reps * 1e3)
 del r_, trace
 torch.cuda.empty_cache()
 
+# ---------------- config 3 with the exchange fused into the LDE (P2P row scatter)
+try:
+  steps, ext, ncols = 1 << 12, 8, 8
+  n = steps * ext
+  g2 = pow(7, (P - 1) // n, P)
+  tr_small = rand_limbs((ncols, steps), 7).to(dev)
+  cl = ncols // world
+  scp = sd.ShardedCommitP2P(eng, ncols, n, dev)
+  root_p, _ = scp.lde_commit(tr_small[rank * cl:(rank + 1) * cl].contiguous(), ext, g2)
+  res["sharded_commit_p2p_ok"] = bool(root_p == want_root)
+  assert root_p == want_root, "fused sharded commit root mismatch"
+  del scp
+  steps, ncols = 1 << 18, 64
+  n = steps * ext
+  g2 = pow(7, (P - 1) // n, P)
+  cl = ncols // world
+  trace = torch.randint(0, 2**31 - 1, (cl, steps, 8), dtype=torch.int32, device=dev)
+  scp = sd.ShardedCommitP2P(eng, ncols, n, dev)
+  for _ in range(2):
+    scp.lde_commit(trace, ext, g2)
+  torch.cuda.synchronize(); dist.barrier()
+  t0 = time.perf_counter()
+  for _ in range(reps):
+    scp.lde_commit(trace, ext, g2)
+  torch.cuda.synchronize()
+  res["cfg3_p2p_lde_merkle_commit_ms"] = tmax((time.perf_counter() - t0) / reps * 1e3)
+  del scp, trace
+  torch.cuda.empty_cache()
+except Exception as ex:
+  import traceback
+  res["p2p_commit_error"] = traceback.format_exc()[-600:]
+
 # ---------------- timing: config 4, one 2^26-point NTT
 logn = 26
 n = 1 << logn

@@ -119,3 +119,35 @@ def test_four_step_fused_exchange_emulated(eng, world, logn):
   assert (out == ref).all()
   for b in recv + [work, outb]:
     b.free()
+
+
+@pytest.mark.parametrize("world,logsteps,ncols", [(2, 9, 4), (4, 10, 8), (8, 12, 8)])
+def test_lde_with_fused_leaf_exchange_emulated(eng, world, logsteps, ncols):
+  """stk_lde_p2p: every emulated rank's LDE scatters its rows into the owners' buffers (G
+  buffers on one GPU); each owner's subtree must be the single-GPU tree's subtree G + r."""
+  from starks_b200.dist import combine_subtree_roots
+  steps, ext = 1 << logsteps, 8
+  n = steps * ext
+  g2 = pow(7, (P - 1) // n, P)
+  rng = np.random.default_rng(world + logsteps)
+  trace = rng.integers(0, 2**32, size=(ncols, steps, 8), dtype=np.uint64).astype(np.uint32)
+  trace[:, :, 7] &= 0x7FFFFFFF
+  d_tr = eng.alloc(trace.nbytes).upload(trace)
+  d_ev = eng.alloc(ncols * n * 32)
+  nodes = eng.alloc(32 * n)
+  root = eng.lde_commit(d_tr.ptr, steps, steps, ext, ncols, g2, d_ev.ptr, n, nodes.ptr)
+  full = nodes.download((n, 32), np.uint8)
+  n_local, cl = n // world, ncols // world
+  bufs = [eng.alloc(ncols * n_local * 32) for _ in range(world)]
+  for r in range(world):
+    eng.lde_p2p(d_tr.at(r * cl * steps * 32), steps, steps, ext, cl, g2, world, r * cl, [b.ptr for b in bufs])
+  roots = []
+  ln = eng.alloc(32 * n_local)
+  for r in range(world):
+    roots.append(eng.merkle_commit(bufs[r].ptr, n_local, ncols, n_local, ln.ptr))
+    loc = ln.download((n_local, 32), np.uint8)
+    for i in (1, 2, n_local // 2 + 1, n_local - 1):
+      dd = i.bit_length() - 1
+      gi = (world + r) * (1 << dd) + (i - (1 << dd))
+      assert (loc[i] == full[gi]).all(), (r, i)
+  assert combine_subtree_roots(roots)[1] == root
