@@ -42,9 +42,9 @@ struct NttPass {
   // distributed (multi-GPU four-step) use: the local array holds the elements of a longer
   // transform of order 2^n_tw whose global index is (J << j_shift) | j_or; the final store
   // goes to local position bitrev_{n_tw}(global J) >> out_shift.  Single-GPU: n_tw = n, rest 0.
-  // zero-padded inputs (LDE): butterfly levels whose half-size is >= 2^zbit see a structurally
-  // zero second operand, (a, 0) -> (a, a*w), and a zero first operand outside the low 2^zbit
-  // residues; those levels skip the add/sub and the dead multiplies.  zbit = 32 disables it.
+  // zero-padded inputs (LDE, n_in <= N/8): the first radix-8 round of the first pass sees one
+  // non-zero element per group and becomes x[m] = x[0] * w^(J*rev3(m)).  zbit = log2 of the
+  // padded input length (32 disables the shortcut).
   int zbit;
   int tw_shift;  // the table is a longer one: entry e lives at W[e << tw_shift]
   int n_tw;
@@ -113,6 +113,19 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
       }
     }
     // exponent of the last (smallest-half) level of this round
+    if (ZS && first && R == 3 && gshift >= A.zbit && gshift == A.n - 3) {
+      // Zero-padded input (LDE, N = 8 * n_in): only x[0] is non-zero and the three levels of
+      // this round reduce to x[m] = x[0] * w^(J0 * rev3(m)) -- seven multiplies, no add/sub,
+      // instead of twelve butterflies on mostly-zero data.
+      if (J0 < (1u << A.zbit)) {
+        const fe x0 = x[0];
+#pragma unroll
+        for (int m = 1; m < M; ++m) {
+          const uint32_t r3 = ((m & 1) << 2) | (m & 2) | ((m >> 2) & 1);
+          x[m] = f.mul_tw(x0, fe_load_ro(A.W + ((unsigned long long)(J0 * r3) << A.tw_shift)));
+        }
+      }
+    } else {
     const int ggs = gshift + A.j_shift;  // log2 of the global index stride of m
     const uint32_t Jl = ((J0 << A.j_shift) | A.j_or) & ((1u << ggs) - 1u);
     const uint32_t er = Jl << (A.n_tw - 1 - ggs);
@@ -127,19 +140,14 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
 #pragma unroll
         for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
           const int i0 = blk * 2 * hm + mm, i1 = i0 + hm;
-          if (ZS && gshift + lh >= A.zbit) {
-            // x[i1] == 0 here; x[i0] != 0 only in the low 2^zbit residues mod 2H
-            const uint32_t res = (J0 + ((uint32_t)i0 << gshift)) & ((2u << (gshift + lh)) - 1u);
-            if (res < (1u << A.zbit)) x[i1] = f.mul_tw(x[i0], tw);
-          } else {
-            fe s = f.add(x[i0], x[i1]);
-            fe d = f.sub(x[i0], x[i1]);
-            x[i0] = s;
-            x[i1] = f.mul_tw(d, tw);
-          }
+          fe s = f.add(x[i0], x[i1]);
+          fe d = f.sub(x[i0], x[i1]);
+          x[i0] = s;
+          x[i1] = f.mul_tw(d, tw);
         }
       }
     }
+    }  // butterfly levels
     if (last && !A.peer_on) {
       if (col_ok) {
         fe* dst = A.out + (unsigned long long)col * A.out_col_stride;

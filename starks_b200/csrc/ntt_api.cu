@@ -357,9 +357,14 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     P.do_scale = (P.final_pass && do_scale) ? 1 : 0;
     P.scale = scale_tw;
     P.zbit = 32;
-    if (i == 0 && n_in > 0 && n_in * 2 <= n && env_int("STK_NTT_ZSKIP", 1)) {
-      int zb = ilog2_u64(n_in);             // 2^zb >= n_in
-      if (zb < P.lo + P.k) P.zbit = zb;     // some level of this pass has half-size >= 2^zb
+    if (i == 0 && n_in > 0 && n_in * 8 <= n && P.k >= 3 && c->is_stark && env_int("STK_NTT_ZSKIP", 1)) {
+      // the top three levels only scale-and-copy: run them as the first (radix-8) round
+      P.zbit = ilog2_u64(n_in);             // 2^zbit >= n_in, and 2^zbit <= N/8
+      if (P.r[0] != 3) {                    // remainder round goes last in this pass
+        int rem = P.r[0];
+        for (int q = 0; q + 1 < P.nrounds; ++q) P.r[q] = P.r[q + 1];
+        P.r[P.nrounds - 1] = rem;
+      }
     }
     if (plan.size() == 1) {
       if (need_tmp) {  // in place: stage the input
