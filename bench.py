@@ -360,7 +360,8 @@ def main():
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_ntt_pass_summary.txt",
                      "alg_bytes_per_launch": alg_bytes / launches_per_step, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                      "kernel": "ntt_pass_kernel<StarkField>", "launches_per_step": launches_per_step,
-                     "alg_bytes_per_step": alg_bytes},
+                     "alg_bytes_per_step": alg_bytes,
+                     "note": "the kernel is bound by the integer pipes, not HBM (256-bit modular butterflies: ~41 int32 op per byte against a machine balance of ~4.7): int_roofline below is the binding one; DRAM is 11.7 % busy in ncu"},
         "int_roofline": {"bound": "int32 pipes", "alg_int32_ops_per_step": int_ops,
                          "achieved_gops": int_ops / (ms_step * 1e-3) / 1e9,
                          "peak_gops": mb.get("imad_iadd3_mixed_gops"), "peak_source": "K0 microbenchmark (IMAD+IADD3 dual issue), same run",
