@@ -119,3 +119,19 @@ def test_single_column_tree_2p23(eng):
     assert len(br) == 24
     leaf = verify_branch(root, i, br)
     assert leaf == limbs_to_be_bytes(x[i].cpu().numpy().view(np.uint32).reshape(1, 8)).tobytes()
+
+
+def test_plain_c_client_of_the_abi(tmp_path):
+  """examples/abi_roundtrip.c: a C program that includes only include/starks_b200.h and links
+  libstarks_b200.so (no Python, no CUDA headers) -- the boundary really is a C ABI."""
+  import os
+  import subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  exe = str(tmp_path / "abi_roundtrip")
+  subprocess.check_call(["/usr/bin/gcc", "-O2", "-I" + os.path.join(root, "include"),
+                         os.path.join(root, "examples", "abi_roundtrip.c"), "-o", exe,
+                         "-L" + os.path.join(root, "starks_b200"), "-lstarks_b200",
+                         "-Wl,-rpath," + os.path.join(root, "starks_b200")])
+  out = subprocess.run([exe], capture_output=True, text=True)
+  assert out.returncode == 0, out.stderr
+  assert out.stdout.startswith("abi roundtrip ok, root=")
