@@ -16,6 +16,19 @@ struct stk_table {
   stk::fe* d;
 };
 
+// validated (root, n, direction) -> derived constants; repeated transforms skip the host
+// exponentiations (an inverse costs two 256-bit modular inversions otherwise)
+struct stk_ntt_consts {
+  stk::fe root;
+  uint64_t n;
+  int inverse;
+  stk::fe w;          // root or root^-1
+  stk::fe scale_tw;   // n^-1 in twiddle form (inverse only)
+  const stk::fe* W = nullptr;  // resolved table (valid while table_gen is unchanged)
+  uint64_t wstride = 1;
+  uint64_t table_gen = ~0ull;
+};
+
 struct stk_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -27,6 +40,8 @@ struct stk_ctx {
   stk::fe p;
   stk::MontField mont;
   std::vector<stk_table> tables;
+  std::vector<stk_ntt_consts> ntt_consts;
+  uint64_t table_gen = 0;  // bumped whenever a table is freed
   void* scratch[8] = {};
   uint64_t scratch_bytes[8] = {};
   std::string err;

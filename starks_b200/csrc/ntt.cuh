@@ -175,9 +175,10 @@ template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, bool ZS = 
 __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, const F f) {
   extern __shared__ __align__(16) uint32_t sm[];
   const uint32_t T = 1u << A.logT;
-  const uint32_t xb = blockIdx.x;
+  // single-pass transforms put the column groups on grid.x (no 65535 limit), tiles otherwise
+  const uint32_t xb = A.c_is_col ? 0u : blockIdx.x;
   const uint32_t Jcta = ((xb & ((1u << A.nl) - 1u)) << A.sl) | ((xb >> A.nl) << A.sh);
-  const uint32_t col0 = A.c_is_col ? (blockIdx.y << A.logC) : blockIdx.y;
+  const uint32_t col0 = A.c_is_col ? (blockIdx.x << A.logC) : blockIdx.y;
   int a = A.k;
   for (int rd = 0; rd < A.nrounds; ++rd) {
     const int r = A.r[rd];

@@ -97,6 +97,8 @@ extern "C" __attribute__((visibility("default"))) int stk_field_set(stk_ctx* c, 
   STK_CUDA(c, cudaStreamSynchronize(c->stream));
   for (auto& t : c->tables) cudaFree(t.d);
   c->tables.clear();
+  c->ntt_consts.clear();
+  ++c->table_gen;
   if (host::is_stark_prime(p)) {
     c->is_stark = true;
     c->p = p;
@@ -164,6 +166,7 @@ int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
     STK_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->tables.front().d);
     c->tables.erase(c->tables.begin());
+    ++c->table_gen;
   }
   stk_table t;
   t.root = root; t.n = n; t.mont = !c->is_stark; t.d = nullptr;
@@ -292,23 +295,39 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
                                 (unsigned long long)n_in, (unsigned long long)n);
   if (n > (1ull << 30)) return stk_fail(c, STK_EUNSUPPORTED, "transform length above 2^30");
-  fe one = host::reduce(host::from_u64(1), c->p);
-  fe rn = stk_h_pow(c, root, n);
-  if (!fe_eq(rn, one)) return stk_fail(c, STK_EINVAL, "root^n != 1: n is not the order of the root");
-  if (n % 2 == 0 && n > 1) {
-    fe rh = stk_h_pow(c, root, n / 2);
-    if (fe_eq(rh, one)) return stk_fail(c, STK_EINVAL, "root has order below n");
+  stk_ntt_consts* K = nullptr;
+  for (auto& e : c->ntt_consts)
+    if (e.n == n && e.inverse == (inverse ? 1 : 0) && fe_eq(e.root, root)) { K = &e; break; }
+  if (!K) {
+    fe one = host::reduce(host::from_u64(1), c->p);
+    fe rn = stk_h_pow(c, root, n);
+    if (!fe_eq(rn, one)) return stk_fail(c, STK_EINVAL, "root^n != 1: n is not the order of the root");
+    if (n % 2 == 0 && n > 1) {
+      fe rh = stk_h_pow(c, root, n / 2);
+      if (fe_eq(rh, one)) return stk_fail(c, STK_EINVAL, "root has order below n");
+    }
+    stk_ntt_consts e;
+    e.root = root; e.n = n; e.inverse = inverse ? 1 : 0;
+    e.w = inverse ? stk_h_inv(c, root) : root;
+    e.scale_tw = fe_zero();
+    if (inverse) e.scale_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(n), c->p)));
+    if (c->ntt_consts.size() >= 64) c->ntt_consts.erase(c->ntt_consts.begin());
+    c->ntt_consts.push_back(e);
+    K = &c->ntt_consts.back();
   }
-  fe w = inverse ? stk_h_inv(c, root) : root;
-  const fe* W = nullptr;
-  uint64_t wstride = 1;
-  STK_TRY(stk_get_table_strided(c, w, n, &W, &wstride));
-  fe scale_tw = fe_zero();
-  int do_scale = inverse && scale;
-  if (do_scale) {
-    fe nn = host::reduce(host::from_u64(n), c->p);
-    scale_tw = stk_h_to_tw(c, stk_h_inv(c, nn));
+  const fe w = K->w;
+  if (K->table_gen != c->table_gen || !K->W) {
+    const fe* Wt = nullptr;
+    uint64_t ws = 1;
+    STK_TRY(stk_get_table_strided(c, w, n, &Wt, &ws));
+    for (auto& e : c->ntt_consts)  // K may have moved if the table build... it does not touch ntt_consts; re-find for safety
+      if (e.n == n && e.inverse == (inverse ? 1 : 0) && fe_eq(e.root, root)) { K = &e; break; }
+    K->W = Wt; K->wstride = ws; K->table_gen = c->table_gen;
   }
+  const fe* W = K->W;
+  uint64_t wstride = K->wstride;
+  const int do_scale = inverse && scale;
+  const fe scale_tw = K->scale_tw;
   bool pow2 = (n & (n - 1)) == 0;
   if (pow2 && (wstride & (wstride - 1))) {  // the pass kernels index by shift
     STK_TRY(stk_get_table(c, w, n, &W));

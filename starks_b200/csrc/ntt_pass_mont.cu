@@ -19,8 +19,9 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   unsigned threads = std::max(1u, T >> MAXR);
   uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
   uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
-  if (cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "batch too large for one launch");
-  dim3 grid((unsigned)tiles, (unsigned)cols);
+  if (!P.c_is_col && cols > 65535) return stk_fail(c, STK_EUNSUPPORTED, "more than 65535 columns of a multi-pass transform");
+  if (cols > 0x7fffffffull) return stk_fail(c, STK_EUNSUPPORTED, "batch too large");
+  dim3 grid(P.c_is_col ? (unsigned)cols : (unsigned)tiles, P.c_is_col ? 1u : (unsigned)cols);
   size_t smem = (P.nrounds > 1 || P.peer_on) ? (size_t)32 * T : 0;
   ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS><<<grid, threads, smem, s>>>(P, f);
   STK_CUDA(c, cudaGetLastError());
