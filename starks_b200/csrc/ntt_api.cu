@@ -216,7 +216,11 @@ static void fill_rounds(NttPass& P, int R) {
 
 // Cuts the n index bits into passes (top bits first) and fixes each pass's tile geometry.
 static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan, int rmax) {
-  const int logT = std::min(10, std::max(6, env_int("STK_NTT_LOGT", 10)));  // tiles of <= 1024 elements
+  // 1024-element tiles (4 CTAs/SM) unless 2048-element tiles (2 CTAs/SM) save a whole pass
+  // over HBM (n = 11, 21, 22): profiles/r01_ntt_plan_sweep2.txt.  Run-time moduli: 1024 only.
+  int want = ((n + 10) / 11 < (n + 9) / 10) ? 11 : 10;
+  if (rmax < 3) want = 10;
+  const int logT = std::min(want, std::max(6, env_int("STK_NTT_LOGT", want)));
   const int kmax = std::min(logT, std::max(3, env_int("STK_NTT_KMAX", 11)));
   plan.clear();
   if (n <= kmax) {
@@ -262,11 +266,14 @@ static int build_plan(int n, uint64_t batch, std::vector<NttPass>& plan, int rma
 // they compile in parallel; this file only sees the host-side launchers.
 int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P);      // radix-8 rounds
 int stk_launch_pass_stark_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);   // + zero-skip levels
+int stk_launch_pass_stark_t11(stk_ctx* c, cudaStream_t s, const NttPass& P);     // 2048-element tiles
+int stk_launch_pass_stark_t11_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);
 int stk_launch_pass_mont(stk_ctx* c, cudaStream_t s, const NttPass& P);       // run-time modulus, radix-4
 
 template <class F>
 static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
   if constexpr (F::kMontgomery) return stk_launch_pass_mont(c, s, P);
+  else if (P.logT > 10) return P.zbit < 32 ? stk_launch_pass_stark_t11_zs(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
   else return P.zbit < 32 ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
 }
 

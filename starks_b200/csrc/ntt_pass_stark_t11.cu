@@ -1,4 +1,4 @@
-// ntt_pass_stark.cu -- one instantiation of the NTT pass kernel and its host-side launcher (split out of
+// ntt_pass_stark_t11.cu -- one instantiation of the NTT pass kernel and its host-side launcher (split out of
 // ntt_api.cu so the heavy kernels compile in parallel).
 #include <algorithm>
 #include "ctx.h"
@@ -28,6 +28,6 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   return STK_OK;
 }
 
-int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P) {
-  return launch_pass_r<StarkField, 3, 128, 4, false>(c, s, P, StarkField());
+int stk_launch_pass_stark_t11(stk_ctx* c, cudaStream_t s, const NttPass& P) {
+  return launch_pass_r<StarkField, 3, 256, 2, false>(c, s, P, StarkField());
 }

@@ -11,11 +11,11 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   static bool attr_done = false;
   if (!attr_done) {
     STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 8 * MAXT));
     attr_done = true;
   }
   const uint32_t T = 1u << P.logT;
-  if (P.logT > 10) return stk_fail(c, STK_EUNSUPPORTED, "tile above 1024 elements");
+  if ((1u << P.logT) > 8u * MAXT) return stk_fail(c, STK_EUNSUPPORTED, "tile larger than this instantiation");
   unsigned threads = std::max(1u, T >> MAXR);
   uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
   uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
