@@ -72,6 +72,10 @@ int stk_memset(stk_ctx* ctx, void* d_dst, int value, uint64_t bytes);
  * the reference test's n = 6 over p = 31) the direct DFT kernel (_simple_ft, :287-300). */
 int stk_ntt(stk_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint64_t in_stride, uint32_t* d_out,
             uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse);
+/* _simple_ft (starks/fft.py:287-300) on its own: the direct O(n^2) DFT for any order n <= 4096
+ * (powers of two included -- an independent cross-check of the fast path). */
+int stk_dft_generic(stk_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint64_t in_stride, uint32_t* d_out,
+                    uint64_t out_stride, uint64_t n, uint64_t batch, const uint32_t root[8], int inverse);
 /* Same, host buffers; columns are streamed through the device in chunks with the copies
  * overlapping the transforms. */
 int stk_ntt_host(stk_ctx* ctx, const uint32_t* h_in, uint64_t n_in, uint64_t in_stride, uint32_t* h_out,

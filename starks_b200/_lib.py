@@ -42,6 +42,7 @@ SIGNATURES = {
     "stk_memcpy_d2d": (cint, [vp, vp, vp, u64]),
     "stk_memset": (cint, [vp, vp, cint, u64]),
     "stk_ntt": (cint, [vp, vp, u64, u64, vp, u64, u64, u64, u32p, cint]),
+    "stk_dft_generic": (cint, [vp, vp, u64, u64, vp, u64, u64, u64, u32p, cint]),
     "stk_ntt_host": (cint, [vp, vp, u64, u64, vp, u64, u64, u64, u32p, cint]),
     "stk_mul_polys": (cint, [vp, vp, u64, vp, u64, vp, u64, u32p]),
     "stk_vec_op": (cint, [vp, cint, vp, vp, vp, u64]),

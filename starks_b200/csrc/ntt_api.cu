@@ -441,6 +441,37 @@ extern "C" __attribute__((visibility("default"))) int stk_ntt(stk_ctx* c, const 
                      inverse, 1);
 }
 
+// _simple_ft (starks/fft.py:287-300) as its own entry point: the direct O(n^2) sum for ANY order
+// n <= 4096 (stk_ntt routes orders that are not a power of two >= 8 here on its own).
+extern "C" __attribute__((visibility("default"))) int stk_dft_generic(stk_ctx* c, const uint32_t* d_in, uint64_t n_in,
+                                                                       uint64_t in_stride, uint32_t* d_out,
+                                                                       uint64_t out_stride, uint64_t n, uint64_t batch,
+                                                                       const uint32_t root[8], int inverse) {
+  if (!c || !d_out || !root || (!d_in && n_in)) return STK_EINVAL;
+  if (n == 0 || batch == 0) return STK_OK;
+  if (n_in > n) return stk_fail(c, STK_EINDEX, "input length exceeds the order of the root");
+  if (n > 4096) return stk_fail(c, STK_EUNSUPPORTED, "direct DFT is limited to orders <= 4096");
+  if ((const void*)d_in == (const void*)d_out) return stk_fail(c, STK_EINVAL, "direct DFT works out of place");
+  fe r = host::reduce(stk_load_fe(root), c->p);
+  fe one = host::reduce(host::from_u64(1), c->p);
+  if (!fe_eq(stk_h_pow(c, r, n), one)) return stk_fail(c, STK_EINVAL, "root^n != 1");
+  fe w = inverse ? stk_h_inv(c, r) : r;
+  const fe* W = nullptr;
+  uint64_t ws = 1;
+  STK_TRY(stk_get_table_strided(c, w, n, &W, &ws));
+  fe scale_tw = fe_zero();
+  if (inverse) scale_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(n), c->p)));
+  unsigned blocks = (unsigned)((n * batch + 127) / 128);
+  if (c->is_stark)
+    dft_generic_kernel<StarkField><<<blocks, 128, 0, c->stream>>>((const fe*)d_in, n_in, in_stride, (fe*)d_out, out_stride,
+                                                                  n, batch, W, ws, inverse ? 1 : 0, scale_tw, StarkField());
+  else
+    dft_generic_kernel<MontField><<<blocks, 128, 0, c->stream>>>((const fe*)d_in, n_in, in_stride, (fe*)d_out, out_stride,
+                                                                 n, batch, W, ws, inverse ? 1 : 0, scale_tw, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
 // Host buffers: columns stream through three device slots, each with its own stream, so that
 // the H2D copy of chunk i+1, the transform of chunk i and the D2H copy of chunk i-1 overlap
 // (PCIe is full duplex; the transform itself is ~5x faster than either copy).

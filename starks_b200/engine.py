@@ -147,6 +147,11 @@ class Engine:
     self._check(self.lib.stk_ntt(self.ctx, d_in, n_in, in_stride, d_out, out_stride, n, batch,
                                  _u32(int_to_limbs(int(root) % self.p)), int(bool(inverse))))
 
+  def dft_generic(self, d_in, n_in, in_stride, d_out, out_stride, n, batch, root, inverse=False):
+    """Direct O(n^2) DFT (stk_dft_generic), any order <= 4096."""
+    self._check(self.lib.stk_dft_generic(self.ctx, d_in, n_in, in_stride, d_out, out_stride, n, batch,
+                                         _u32(int_to_limbs(int(root) % self.p)), int(bool(inverse))))
+
   def ntt_host(self, cols, n, root, inverse=False, out=None):
     """cols: (batch, n_in, 8) uint32 host array -> (batch, n, 8) uint32 (stk_ntt_host)."""
     cols = np.ascontiguousarray(cols, dtype=np.uint32)

@@ -135,3 +135,23 @@ def test_plain_c_client_of_the_abi(tmp_path):
   out = subprocess.run([exe], capture_output=True, text=True)
   assert out.returncode == 0, out.stderr
   assert out.stdout.startswith("abi roundtrip ok, root=")
+
+
+def test_direct_dft_cross_checks_the_fast_path(eng, oracle):
+  """stk_dft_generic (the reference's _simple_ft, any order) against the radix-8 passes and the
+  oracle, on power-of-two and non-power-of-two orders."""
+  for n in (8, 64, 512):
+    w = pow(7, (P - 1) // n, P)
+    x = rand((2, n), n)
+    d_in, d_a, d_b = eng.alloc(x.nbytes).upload(x), eng.alloc(x.nbytes), eng.alloc(x.nbytes)
+    for inv in (False, True):
+      eng.ntt(d_in.ptr, n, n, d_a.ptr, n, n, 2, w, inverse=inv)
+      eng.dft_generic(d_in.ptr, n, n, d_b.ptr, n, n, 2, w, inverse=inv)
+      a, b = d_a.download((2, n, 8)), d_b.download((2, n, 8))
+      assert (a == b).all() and (a == oracle.fft_limbs(P, w, x, n, inv=inv)).all()
+  eng.set_field(31)
+  x = oracle.to_limbs([7, 0, 30, 4, 11, 2]).reshape(1, 6, 8)
+  d_in, d_o = eng.alloc(x.nbytes).upload(x), eng.alloc(x.nbytes)
+  eng.dft_generic(d_in.ptr, 6, 6, d_o.ptr, 6, 6, 1, pow(3, 5, 31))
+  assert oracle.from_limbs(d_o.download((6, 8))) == oracle.fft_1d(31, [7, 0, 30, 4, 11, 2], pow(3, 5, 31))
+  eng.set_field(P)
