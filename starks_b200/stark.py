@@ -9,6 +9,7 @@ branch gathers (stk_merkle_paths) and FRI folds (stk_fri_fold4).  Only 32-byte r
 Fiat-Shamir scalars and the opened branches cross to the host.  The proof object
 [m_root, l_root, branches, fri_proof] (stark.py:270-277) is bit-identical to the reference's.
 verify_proof is host-side glue (80 positions + FRI checks) mirroring stark.py:281-372."""
+import ctypes
 import time
 from hashlib import blake2s
 
@@ -103,7 +104,10 @@ class STARK(object):
     mark("upload")
     # construct_trace_polynomials (:27-36) + evaluation (:254-256)
     eng.lde(d_trace.ptr, steps, steps, ext, w, G2, d_cols.ptr, N, d_coeffs=d_pcoef.ptr, coeff_stride=steps)
-    # construct_constraint_polynomials (:38-55), evaluation form
+    # construct_constraint_polynomials (:38-55), evaluation form -- on the SMALLEST subgroup
+    # that determines C: deg C <= d*(steps-1) < M = steps*2^ceil(log2 d), so C (and D = C/Z)
+    # are recovered exactly from M evaluations; only D's final evaluation runs at size N.
+    # On <G_M>, G_M = G2^(N/M), P_j(G1*x_k) is the evaluation M/steps places further on.
     mono_out, mono_coef, mono_exp = [], [], []
     for j, ms in enumerate(self._monomials):
       for exps, c in ms:
@@ -114,22 +118,31 @@ class STARK(object):
     h_out = np.asarray(mono_out, dtype=np.uint32)
     h_coef = ints_to_limbs(mono_coef) if nm else np.zeros((0, 8), np.uint32)
     h_exp = np.asarray(mono_exp, dtype=np.uint8).reshape(nm, w) if nm else np.zeros((0, w), np.uint8)
-    eng._check(eng.lib.stk_constraint_eval(eng.ctx, d_cols.ptr, N, ext, w, N, h_out.ctypes.data, h_coef.ctypes.data,
-                                           h_exp.ctypes.data, nm, d_t1.ptr, N))
+    mult = 1
+    while mult < max(self.get_degree(), 1):
+      mult *= 2
+    M = min(N, steps * mult)
+    if M == N:
+      pev_ptr, pev_stride = d_cols.ptr, N
+    else:
+      GM = pow(G2, N // M, p)
+      eng.ntt(d_pcoef.ptr, steps, steps, d_t2.ptr, M, M, w, GM)
+      pev_ptr, pev_stride = d_t2.ptr, M
+    eng._check(eng.lib.stk_constraint_eval(eng.ctx, pev_ptr, M, M // steps, w, pev_stride, h_out.ctypes.data,
+                                           h_coef.ctypes.data, h_exp.ctypes.data, nm, d_t1.ptr, M))
     # construct_remainder_polynomials (:57-78): D = C / Z in coefficient form
-    eng.ntt(d_t1.ptr, N, N, d_t2.ptr, N, N, w, G2, inverse=True)
-    import ctypes
+    eng.ntt(d_t1.ptr, M, M, d_t2.ptr, M, M, w, pow(G2, N // M, p), inverse=True)
     bad = ctypes.c_uint32(0)
     last_l = int_to_limbs(last)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
     for j in range(w):
-      eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * N * E), N, steps, last_l.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
-                                        d_t1.at(j * N * E), ctypes.byref(bad)))
+      eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
+                                        d_t1.at(j * M * E), ctypes.byref(bad)))
       assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
-    eng.ntt(d_t1.ptr, N, N, d_cols.at(w * N * E), N, N, w, G2)
+    eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
     # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
     out_vals = limbs_to_ints(tr[:, -1, :])
     one_l = int_to_limbs(1)
-    u32p = ctypes.POINTER(ctypes.c_uint32)
     for j in range(w):
       (_, _, input_value) = boundary[j]
       interp = _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
