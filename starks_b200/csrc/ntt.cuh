@@ -78,7 +78,10 @@ struct NttPass {
 // that for every radix-8 round (consecutive lanes differ in bits [0,q) and [q+3, ...)).
 __device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >> 3) & 7u); }
 
-template <class F, int R, bool ZS>
+// TRIV: the round's lowest level has global stride 1 (last round of the final pass of a whole
+// transform), so its exponent base is 0 and every mm == 0 twiddle is w^0 = 1: 7 of the 12
+// multiplies of a radix-8 round (3 of 4 for radix-4, the only one for radix-2) are skipped.
+template <class F, int R, bool ZS, bool TRIV>
 __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
                                           uint32_t Jcta, uint32_t col0, int a, bool first, bool last) {
   constexpr int M = 1 << R;
@@ -135,15 +138,17 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
       const int hm = 1 << lh;
 #pragma unroll
       for (int mm = 0; mm < hm; ++mm) {
+        const bool unit = TRIV && mm == 0;  // er == 0 here
         const uint32_t e = (er >> lh) + ((uint32_t)mm << (A.n_tw - 1 - lh));
-        const fe tw = fe_load_ro(A.W + ((unsigned long long)e << A.tw_shift));
+        fe tw;
+        if (!unit) tw = fe_load_ro(A.W + ((unsigned long long)e << A.tw_shift));
 #pragma unroll
         for (int blk = 0; blk < (M >> (lh + 1)); ++blk) {
           const int i0 = blk * 2 * hm + mm, i1 = i0 + hm;
           fe s = f.add(x[i0], x[i1]);
           fe d = f.sub(x[i0], x[i1]);
           x[i0] = s;
-          x[i1] = f.mul_tw(d, tw);
+          x[i1] = unit ? d : f.mul_tw(d, tw);
         }
       }
     }
@@ -184,9 +189,13 @@ __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, c
     const int r = A.r[rd];
     a -= r;
     const bool first = rd == 0, last = rd == A.nrounds - 1;
-    if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2), ZS>(A, f, sm, T, Jcta, col0, a, first, last);
-    else if (r == 2) ntt_round<F, 2, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
-    else ntt_round<F, 1, ZS>(A, f, sm, T, Jcta, col0, a, first, last);
+    if (last && A.lo + a + A.j_shift == 0) {  // global stride 1: unit twiddles (see TRIV)
+      if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2), ZS, true>(A, f, sm, T, Jcta, col0, a, first, last);
+      else if (r == 2) ntt_round<F, 2, ZS, true>(A, f, sm, T, Jcta, col0, a, first, last);
+      else ntt_round<F, 1, ZS, true>(A, f, sm, T, Jcta, col0, a, first, last);
+    } else if (MAXR >= 3 && r == 3) ntt_round<F, (MAXR >= 3 ? 3 : 2), ZS, false>(A, f, sm, T, Jcta, col0, a, first, last);
+    else if (r == 2) ntt_round<F, 2, ZS, false>(A, f, sm, T, Jcta, col0, a, first, last);
+    else ntt_round<F, 1, ZS, false>(A, f, sm, T, Jcta, col0, a, first, last);
     if (!last) __syncthreads();
   }
   if (A.peer_on == 2) {

@@ -207,10 +207,17 @@ static int ilog2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) ++l; retur
 
 static int ntt_max_radix() { return 3; }  // radix-4 measured no faster: profiles/r01_ntt_radix_sweep.txt
 
+// Rounds of a pass.  Where the remainder round (k mod R levels) goes was measured
+// (tests/gpu_knobs.py, profiles/r01_ntt_round_order.txt): last in non-final passes and in
+// 1024-element final passes, first in 2048-element final passes; the spread is 1-3 %.
 static void fill_rounds(NttPass& P, int R) {
-  int k = P.k, rem = k % R, idx = 0;
-  if (rem) P.r[idx++] = rem;
-  for (int i = 0; i < k / R; ++i) P.r[idx++] = R;
+  int k = P.k, rem = k % R, full = k / R, idx = 0;
+  int pos = P.final_pass ? env_int("STK_NTT_REMPOS_FINAL", P.logT > 10 ? 0 : 9) : env_int("STK_NTT_REMPOS", 9);
+  if (pos > full) pos = full;
+  for (int i = 0; i <= full; ++i) {
+    if (i == pos && rem) P.r[idx++] = rem;
+    if (i < full) P.r[idx++] = R;
+  }
   P.nrounds = idx;
 }
 
