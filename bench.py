@@ -155,6 +155,15 @@ def extras(eng, torch, stream, local):
   for _ in range(reps):
     root = eng.lde_commit(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n, d_nodes.data_ptr())
   out["lde_merkle_commit_ms_64x2^18_x8"] = (time.perf_counter() - t0) / reps * 1e3
+  # same call with the Merkle bottom level hashed inside the transform's final pass (opt-in)
+  os.environ["STK_FUSED_HASH"] = "1"
+  eng.lde_commit(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n, d_nodes.data_ptr())
+  t0 = time.perf_counter()
+  for _ in range(reps):
+    root_u = eng.lde_commit(d_tr.data_ptr(), steps, steps, ext, ncols, g2, d_ev.data_ptr(), n, d_nodes.data_ptr())
+  out["lde_merkle_commit_ms_fused_leaf_hash"] = (time.perf_counter() - t0) / reps * 1e3
+  del os.environ["STK_FUSED_HASH"]
+  assert root_u == root, "fused and separate leaf hashing disagree"
   # split: LDE alone / commit alone (CUDA events on the launching stream)
   e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
   with torch.cuda.stream(stream):

@@ -154,6 +154,16 @@ int reduce_levels(stk_ctx* c, uint32_t* nodes, uint64_t np) {
 
 #define STK_API extern "C" __attribute__((visibility("default")))
 
+int stk_merkle_finish(stk_ctx* c, uint8_t* d_nodes, uint64_t np, uint8_t* h_root) {
+  STK_CUDA(c, cudaMemsetAsync(d_nodes, 0, 32, c->stream));
+  STK_TRY(reduce_levels(c, (uint32_t*)d_nodes, np));
+  if (h_root) {
+    STK_CUDA(c, cudaMemcpyAsync(h_root, d_nodes + 32, 32, cudaMemcpyDeviceToHost, c->stream));
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return STK_OK;
+}
+
 STK_API int stk_merkle_commit(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
                               uint8_t* d_nodes, uint8_t* h_root) {
   if (!c || !d_cols || !d_nodes || ncols == 0) return STK_EINVAL;

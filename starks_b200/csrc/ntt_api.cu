@@ -276,10 +276,12 @@ int stk_launch_pass_stark_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);   //
 int stk_launch_pass_stark_t11(stk_ctx* c, cudaStream_t s, const NttPass& P);     // 2048-element tiles
 int stk_launch_pass_stark_t11_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);
 int stk_launch_pass_mont(stk_ctx* c, cudaStream_t s, const NttPass& P);       // run-time modulus, radix-4
+int stk_launch_pass_stark_hash(stk_ctx* c, cudaStream_t s, const NttPass& P);  // final pass + Merkle bottom level
 
 template <class F>
 static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
   if constexpr (F::kMontgomery) return stk_launch_pass_mont(c, s, P);
+  else if (P.hash_on) return stk_launch_pass_stark_hash(c, s, P);
   else if (P.logT > 10) return P.zbit < 32 ? stk_launch_pass_stark_t11_zs(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
   else return P.zbit < 32 ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
 }
@@ -304,7 +306,7 @@ __global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stri
 
 static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_in, uint64_t n_in, uint64_t in_stride,
                       fe* d_out, uint64_t out_stride, uint64_t n, uint64_t batch, const fe& root, int inverse,
-                      int scale, const stk_peer_leaf* peer = nullptr) {
+                      int scale, const stk_peer_leaf* peer = nullptr, uint32_t* hash_nodes = nullptr) {
   if (n == 0 || batch == 0) return STK_OK;
   if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
                                 (unsigned long long)n_in, (unsigned long long)n);
@@ -376,6 +378,8 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   fe* tmp = nullptr;
   if (peer && (plan.size() < 2 || logn - 2 - peer->g < plan.back().logC))
     return stk_fail(c, STK_EUNSUPPORTED, "peer scatter needs a multi-pass transform (N >= 2^11) and N/4G >= tile width");
+  if (hash_nodes && !stk_ntt_can_fuse_hash(c, n, batch))
+    return stk_fail(c, STK_EUNSUPPORTED, "fused leaf hash: transform shape not eligible");
   bool need_tmp = plan.size() > 1 || (const void*)d_in == (const void*)d_out;
   if (need_tmp) {
     void* t;
@@ -423,11 +427,37 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
         P.peer_on = 2; P.peer_g = peer->g; P.peer_col0 = peer->col0;
         for (int r2 = 0; r2 < (1 << peer->g); ++r2) P.peer_out[r2] = (fe*)(uintptr_t)peer->ptrs[r2];
       }
+      if (hash_nodes) {  // one counter per tile, zeroed in stream order before the pass
+        const uint64_t tiles = n >> P.logT;
+        void* cnt;
+        STK_TRY(stk_scratch(c, 3, tiles * sizeof(unsigned int), &cnt));
+        STK_CUDA(c, cudaMemsetAsync(cnt, 0, tiles * sizeof(unsigned int), s));
+        P.hash_on = 1; P.grid_swap = 1; P.hash_nodes = hash_nodes; P.hash_cnt = (unsigned int*)cnt;
+      }
     }
     if (c->is_stark) STK_TRY(launch_pass<StarkField>(c, s, P, StarkField()));
     else STK_TRY(launch_pass<MontField>(c, s, P, c->mont));
   }
   return STK_OK;
+}
+
+// The final pass can also hash the Merkle bottom level when it is a multi-pass transform over
+// the STARK prime whose tiles fit grid.y and hold whole permute4 quads (k >= 2).
+bool stk_ntt_can_fuse_hash(stk_ctx* c, uint64_t n, uint64_t batch) {
+  if (!c->is_stark || n < 8 || (n & (n - 1)) || batch == 0 || batch > 0x7fffffffull) return false;
+  // Opt-in: measured SLOWER than the separate leaf kernel on B200 (64 x 2^21: 24.4 vs 23.3 ms,
+  // DESIGN.md section 4) -- the pass kernel fills the register file at 16 warps/SM, so hashing
+  // CTAs displace butterfly CTAs instead of filling their idle ALU slots.
+  if (!env_int("STK_FUSED_HASH", 0)) return false;
+  std::vector<NttPass> plan;
+  if (build_plan(ilog2_u64(n), batch, plan, ntt_max_radix()) != STK_OK || plan.size() < 2) return false;
+  const NttPass& L = plan.back();
+  return L.k >= 2 && L.nrounds >= 2 && (n >> L.logT) <= 65535;
+}
+
+int stk_ntt_dev_hash(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, fe* d_out, uint64_t out_stride,
+                     uint64_t n, uint64_t batch, const fe& root, uint32_t* d_nodes) {
+  return ntt_dev_on(c, c->stream, 0, d_in, n_in, in_stride, d_out, out_stride, n, batch, root, 0, 0, nullptr, d_nodes);
 }
 
 int stk_ntt_dev_peer(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, uint64_t n, uint64_t batch,

@@ -4,6 +4,8 @@ Host code above the C ABI.  Device memory is owned either by the library
 (`Engine.alloc`) or by torch tensors whose `data_ptr()` is passed straight through;
 nothing here computes on the CPU."""
 import ctypes
+import functools
+import struct
 import threading
 
 import numpy as np
@@ -235,10 +237,9 @@ class Engine:
     out = np.empty((k, rec), dtype=np.uint8)
     self._check(self.lib.stk_merkle_paths(self.ctx, d_cols, n, ncols, col_stride, d_nodes, idx.ctypes.data, k,
                                           out.ctypes.data, rec))
-    res = []
-    for r in out:
-      b = r.tobytes()
-      res.append([b[:L], b[L:2 * L]] + [b[2 * L + 32 * j:2 * L + 32 * (j + 1)] for j in range(depth - 1)])
+    # one C call splits every record into its [leaf, sibling leaf, nodes...] bytes objects
+    S = _path_struct(L, depth)
+    res = [list(t) for t in S.iter_unpack(out.tobytes())]
     return res
 
   def fri_fold4(self, d_vals, n, root, special_x, d_out):
@@ -249,6 +250,11 @@ class Engine:
     ms, ops = ctypes.c_float(), ctypes.c_double()
     self._check(self.lib.stk_microbench(self.ctx, which, iters, ctypes.byref(ms), ctypes.byref(ops)))
     return ms.value, ops.value
+
+
+@functools.lru_cache(maxsize=None)
+def _path_struct(L, depth):
+  return struct.Struct("%ds%ds" % (L, L) + "32s" * (depth - 1))
 
 
 def _u32(arr):

@@ -124,6 +124,8 @@ class STARK(object):
     M = min(N, steps * mult)
     if M == N:
       pev_ptr, pev_stride = d_cols.ptr, N
+    elif M == steps:
+      pev_ptr, pev_stride = d_trace.ptr, steps   # P_j on <G1> is the witness column itself
     else:
       GM = pow(G2, N // M, p)
       eng.ntt(d_pcoef.ptr, steps, steps, d_t2.ptr, M, M, w, GM)
