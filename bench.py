@@ -111,6 +111,30 @@ class ClockSampler(threading.Thread):
             "samples": len(s), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def pcie_duplex_ceiling(torch, local):
+  """Pinned H2D and D2H copies of 512 MiB at once on two streams: GB/s per direction."""
+  nbytes = 1 << 29
+  dev = "cuda:%d" % local
+  h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+  h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+  d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+  d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+  s1, s2 = torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)
+  best = 0.0
+  for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+      with torch.cuda.stream(s1):
+        d_a.copy_(h_in, non_blocking=True)
+      with torch.cuda.stream(s2):
+        h_out.copy_(d_b, non_blocking=True)
+    torch.cuda.synchronize()
+    if rep:
+      best = max(best, 2 * nbytes / (time.perf_counter() - t0) / 1e9)
+  return best
+
+
 def synth_columns(cols, n, seed):
   import numpy as np
   rng = np.random.default_rng(seed)
@@ -315,7 +339,7 @@ def main():
   ms = e0.elapsed_time(e1)
   clocks = sampler.stop()
   # e2e through the host-buffer API
-  e2e_s = None
+  e2e_s, pcie_duplex = None, None
   if not args.no_e2e:
     e2e_steps = max(1, min(args.steps, 5))
     eng.ntt_host(host_in.array, N, w, out=host_out.array)  # warm
@@ -325,6 +349,7 @@ def main():
       eng.ntt_host(host_in.array, N, w, out=host_out.array)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    pcie_duplex = pcie_duplex_ceiling(torch, local)
   if world > 1:
     t = torch.tensor([ms, e2e_s or 0.0], dtype=torch.float64, device="cuda:%d" % local)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -380,7 +405,11 @@ def main():
     }
     if e2e_s is not None:
       line["e2e"] = {"value": elems / e2e_s / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": cols * N * 32,
-                     "d2h_bytes_per_step": cols * N * 32, "ms_per_step": e2e_s * 1e3}
+                     "d2h_bytes_per_step": cols * N * 32, "ms_per_step": e2e_s * 1e3,
+                     "gb_per_s_each_way": cols * N * 32 / e2e_s / 1e9,
+                     "pcie_duplex_ceiling_gb_per_s_each_way": pcie_duplex,
+                     "note": "host-buffer API (stk_ntt_host): three-slot H2D / transform / D2H pipeline; bound by PCIe, "
+                             "ceiling = plain pinned copies both ways at once, measured in this run"}
     if not args.no_extras:
       try:
         line["extra"] = extras(eng, torch, stream, local)

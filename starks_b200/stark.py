@@ -97,13 +97,10 @@ class STARK(object):
     assert tr.shape[1] == steps
     E = 32
     d_trace = eng.alloc(w * steps * E).upload(tr)
-    d_pcoef = eng.alloc(w * steps * E)
     d_cols = eng.alloc(3 * w * N * E)        # rows: P_1..P_w, D_1..D_w, B_1..B_w (stark.py:247)
     d_t1 = eng.alloc(w * N * E)
     d_t2 = eng.alloc(w * N * E)
     mark("upload")
-    # construct_trace_polynomials (:27-36) + evaluation (:254-256)
-    eng.lde(d_trace.ptr, steps, steps, ext, w, G2, d_cols.ptr, N, d_coeffs=d_pcoef.ptr, coeff_stride=steps)
     # construct_constraint_polynomials (:38-55), evaluation form -- on the SMALLEST subgroup
     # that determines C: deg C <= d*(steps-1) < M = steps*2^ceil(log2 d), so C (and D = C/Z)
     # are recovered exactly from M evaluations; only D's final evaluation runs at size N.
@@ -122,42 +119,61 @@ class STARK(object):
     while mult < max(self.get_degree(), 1):
       mult *= 2
     M = min(N, steps * mult)
+    GM = pow(G2, N // M, p)
+    # When every coefficient vector is short enough for the zero-padded transform (M <= N/8) the
+    # 3w columns P, D, B are evaluated by ONE batched transform at the end; otherwise P goes
+    # first (the constraints may need its size-N evaluations) and D, B follow on their own.
+    merged = M * 8 <= N
+    cs = M if merged else steps                 # coefficient row stride
+    d_coef = eng.alloc((3 * w if merged else w) * cs * E)
+    if merged and cs > steps:
+      eng._check(eng.lib.stk_memset(eng.ctx, d_coef.ptr, 0, 3 * w * cs * E))
+    # construct_trace_polynomials (:27-36): inverse transform over <G1>
+    eng.ntt(d_trace.ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
+    if not merged:
+      eng.ntt(d_coef.ptr, steps, cs, d_cols.ptr, N, N, w, G2)            # evaluation of P (:254-256)
     if M == N:
       pev_ptr, pev_stride = d_cols.ptr, N
     elif M == steps:
       pev_ptr, pev_stride = d_trace.ptr, steps   # P_j on <G1> is the witness column itself
     else:
-      GM = pow(G2, N // M, p)
-      eng.ntt(d_pcoef.ptr, steps, steps, d_t2.ptr, M, M, w, GM)
+      eng.ntt(d_coef.ptr, steps, cs, d_t2.ptr, M, M, w, GM)
       pev_ptr, pev_stride = d_t2.ptr, M
     eng._check(eng.lib.stk_constraint_eval(eng.ctx, pev_ptr, M, M // steps, w, pev_stride, h_out.ctypes.data,
                                            h_coef.ctypes.data, h_exp.ctypes.data, nm, d_t1.ptr, M))
     # construct_remainder_polynomials (:57-78): D = C / Z in coefficient form
-    eng.ntt(d_t1.ptr, M, M, d_t2.ptr, M, M, w, pow(G2, N // M, p), inverse=True)
+    eng.ntt(d_t1.ptr, M, M, d_t2.ptr, M, M, w, GM, inverse=True)
     bad = ctypes.c_uint32(0)
     last_l = int_to_limbs(last)
     u32p = ctypes.POINTER(ctypes.c_uint32)
     for j in range(w):
+      dst = d_coef.at((w + j) * cs * E) if merged else d_t1.at(j * M * E)
       eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
-                                        d_t1.at(j * M * E), ctypes.byref(bad)))
+                                        dst, ctypes.byref(bad)))
       assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
-    eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
+    if not merged:
+      eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
     # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
     out_vals = limbs_to_ints(tr[:, -1, :])
     one_l = int_to_limbs(1)
+    interps = []
     for j in range(w):
       (_, _, input_value) = boundary[j]
-      interp = _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
-      d_i = eng.alloc(2 * E).upload(ints_to_limbs(interp))
-      a = d_t2.at(j * steps * E)
-      eng._check(eng.lib.stk_memcpy_d2d(eng.ctx, a, d_pcoef.at(j * steps * E), steps * E))
-      eng._check(eng.lib.stk_vec_op(eng.ctx, 1, a, d_i.ptr, a, 2))
-      q1 = d_t1.at(j * steps * E)
+      interps += _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
+    d_i = eng.alloc(2 * w * E).upload(ints_to_limbs(interps))
+    for j in range(w):
+      a = d_coef.at((2 * w + j) * cs * E) if merged else d_t2.at(j * steps * E)
+      eng._check(eng.lib.stk_memcpy_d2d(eng.ctx, a, d_coef.at(j * cs * E), steps * E))
+      eng._check(eng.lib.stk_vec_op(eng.ctx, 1, a, d_i.at(2 * j * E), a, 2))
+      q1 = d_t1.at(j * steps * E)   # free again: its last reader is already enqueued on the stream
       eng._check(eng.lib.stk_div_linear(eng.ctx, a, steps, one_l.ctypes.data_as(u32p), 1, q1))
       eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
-      eng.sync()
-      d_i.free()
-    eng.ntt(d_t2.ptr, steps - 2, steps, d_cols.at(2 * w * N * E), N, N, w, G2)
+      if merged:   # the quotient has steps-2 coefficients; clear the two stale ones above it
+        eng._check(eng.lib.stk_memset(eng.ctx, a + (steps - 2) * E, 0, 2 * E))
+    if merged:
+      eng.ntt(d_coef.ptr, cs, cs, d_cols.ptr, N, N, 3 * w, G2)           # evaluation of P, D, B (:254-256)
+    else:
+      eng.ntt(d_t2.ptr, steps - 2, steps, d_cols.at(2 * w * N * E), N, N, w, G2)
     mark("enqueue_polys")
     # merkelize_polynomial_evaluations (:257)
     d_mnodes = eng.alloc(32 * N)
@@ -198,9 +214,9 @@ class STARK(object):
     for (a, ta), (b, tb) in zip(marks[:-1], marks[1:]):
       self.timings[b + "_ms"] = (tb - ta) * 1e3
     if keep_device:
-      self.device = dict(cols=d_cols, pcoef=d_pcoef, l=d_l, mnodes=d_mnodes, lnodes=d_lnodes)
+      self.device = dict(cols=d_cols, pcoef=d_coef, l=d_l, mnodes=d_mnodes, lnodes=d_lnodes)
     else:
-      for b in (d_trace, d_pcoef, d_cols, d_t1, d_t2, d_mnodes, d_l, d_lnodes):
+      for b in (d_trace, d_coef, d_i, d_cols, d_t1, d_t2, d_mnodes, d_l, d_lnodes):
         b.free()
     return proof
 
