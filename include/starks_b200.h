@@ -155,6 +155,18 @@ int stk_merkle_paths(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t 
  * reference does not reduce it, fri.py:229). */
 int stk_fri_fold4(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, const uint32_t root[8],
                   const uint32_t special_x[8], uint32_t* d_out);
+/* The whole commit phase of SmoothSubgroupFRI.generate_proximity_proof (starks/fri.py:189-266)
+ * for evaluations already on the device: per layer fold, column tree, Fiat-Shamir indices
+ * (starks/utils.py:60-90) and branch gathers, one host synchronisation per layer.  d_nodes0 /
+ * h_root0: the tree over d_vals0 if the caller has built it (both NULL: built here).
+ * h_out receives, per fold layer: root2 (32 B) | k column-tree records (branch of y) | 4k
+ * records of the layer's own tree (y, y+q, y+2q, y+3q per y); then the last layer's values
+ * as 32-byte big-endian words.  k = security for the first layer, 40 below it (fri.py:262-266).
+ * Records are stk_merkle_paths records.  *out_len = bytes needed / written; n0 a power of two. */
+int stk_fri_prove(stk_ctx* ctx, const uint32_t* d_vals0, uint64_t n0, const uint8_t* d_nodes0,
+                  const uint8_t* h_root0, const uint32_t root[8], uint64_t maxdeg_plus_1,
+                  uint64_t exclude_multiples_of, uint64_t security, uint8_t* h_out, uint64_t out_cap,
+                  uint64_t* out_len);
 
 /* ---- prover constructions between the commitments (starks/stark.py:38-177) ---------- */
 /* construct_constraint_polynomials in evaluation form (stark.py:38-55):
@@ -179,6 +191,14 @@ int stk_div_linear(stk_ctx* ctx, const uint32_t* d_a, uint64_t n, const uint32_t
  * out[i] = sum_c weights[c] * cols[c][i]. */
 int stk_lincomb(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
                 const uint32_t* h_weights, uint32_t* d_out);
+/* get_computational_trace (starks/air.py:31-52) with the witness transposition of
+ * AIR.generate_witness (:124): h_witness[dim][step] (width x steps elements, host memory --
+ * ideally from stk_host_alloc), state[0] = h_inp, state[i+1][j] = step_poly_j(state[i]).  Step
+ * polynomials as the monomial list of stk_constraint_eval.  Sequential recurrence: runs on the
+ * calling host thread. */
+int stk_trace_generate(stk_ctx* ctx, const uint32_t* h_inp, uint64_t steps, uint64_t width,
+                       const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs, const uint8_t* h_mono_exps,
+                       uint64_t nmono, uint32_t* h_witness);
 
 /* ---- K0: integer-pipe microbenchmarks (roofline denominators) ---------------------- */
 /* which: 0 IMAD, 1 IMAD.WIDE, 2 IADD3, 3 IMAD.HI, 4 IADD3+LOP3+SHF (BLAKE2s mix),

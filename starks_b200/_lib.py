@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarks_b200.so")
+# STARKS_B200_LIB: an alternative build of the same ABI (kernel A/B experiments only)
+LIB_PATH = os.environ.get("STARKS_B200_LIB") or os.path.join(_HERE, "libstarks_b200.so")
 
 STK_OK, STK_EINVAL, STK_ECUDA, STK_EUNSUPPORTED, STK_EINDEX = 0, 1, 2, 3, 4
 
@@ -56,10 +57,12 @@ SIGNATURES = {
     "stk_merkle_commit_raw": (cint, [vp, vp, u64, u64, vp, vp]),
     "stk_merkle_paths": (cint, [vp, vp, u64, u64, u64, vp, vp, u64, vp, u64]),
     "stk_fri_fold4": (cint, [vp, vp, u64, u32p, u32p, vp]),
+    "stk_fri_prove": (cint, [vp, vp, u64, vp, vp, u32p, u64, u64, u64, vp, u64, vp]),
     "stk_constraint_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, vp, u64]),
     "stk_quotient_z": (cint, [vp, vp, u64, u64, u32p, vp, ctypes.POINTER(ctypes.c_uint32)]),
     "stk_div_linear": (cint, [vp, vp, u64, u32p, u64, vp]),
     "stk_lincomb": (cint, [vp, vp, u64, u64, u64, vp, vp]),
+    "stk_trace_generate": (cint, [vp, vp, u64, u64, vp, vp, vp, u64, vp]),
     "stk_microbench": (cint, [vp, cint, u64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -189,6 +189,26 @@ struct StarkField {
     // fold 1:  L + H*2^256 = L + (351*H << 32) - H
     // U = 351*H (9 limbs): even limbs of H give four non-overlapping 41-bit products,
     // the odd ones are accumulated one limb up in a single carry chain.
+#ifdef STK_REDUCE_SPLIT
+    // Measured alternative (tests/gpu_altlib.py): 351*H as two sets of four independent 41-bit
+    // products (even limbs, odd limbs one up) merged by two add chains -- no accumulating wide
+    // multiply, no register-pair realignment moves.  +2 % on the in-register butterfly
+    // (87.9 -> 89.7 G/s), nothing on the transform (8.82 vs 8.84 ms): not the default.
+    uint32_t UE[8], UO[8];
+    mul_row_first(UE, H, 351u);
+    mul_row_first(UO, H + 1, 351u);
+    uint32_t B[10];
+    B[0] = L[0];
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(B[1]) : "r"(L[1]), "r"(UE[0]));
+#pragma unroll
+    for (int i = 2; i < 8; ++i) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(B[i]) : "r"(L[i]), "r"(UE[i - 1]));
+    asm volatile("addc.cc.u32 %0, %1, 0;" : "=r"(B[8]) : "r"(UE[7]));
+    asm volatile("addc.u32 %0, 0, 0;" : "=r"(B[9]));
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(B[2]) : "r"(UO[0]));
+#pragma unroll
+    for (int i = 3; i < 9; ++i) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(B[i]) : "r"(UO[i - 2]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(B[9]) : "r"(UO[7]));
+#else
     uint32_t U[10];
     U[8] = 0;
     mul_row_first(U, H, 351u);
@@ -200,6 +220,7 @@ struct StarkField {
     for (int i = 2; i < 8; ++i) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(B[i]) : "r"(L[i]), "r"(U[i - 1]));
     asm volatile("addc.cc.u32 %0, %1, 0;" : "=r"(B[8]) : "r"(U[7]));
     asm volatile("addc.u32 %0, %1, 0;" : "=r"(B[9]) : "r"(U[8]));
+#endif
     asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(B[0]) : "r"(H[0]));
 #pragma unroll
     for (int i = 1; i < 8; ++i) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(B[i]) : "r"(H[i]));

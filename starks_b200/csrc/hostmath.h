@@ -104,7 +104,16 @@ inline fe powmod(const fe& a, const fe& e, const fe& p) {
   }
   return r;
 }
-inline fe pow_u64(const fe& a, uint64_t e, const fe& p) { return powmod(a, from_u64(e), p); }
+// small exponents (strides, orders): stop at the top bit instead of walking all 256
+inline fe pow_u64(const fe& a, uint64_t e, const fe& p) {
+  fe r = reduce(from_u64(1), p);
+  fe base = a;
+  for (; e; e >>= 1) {
+    if (e & 1) r = mulmod(r, base, p);
+    if (e > 1) base = mulmod(base, base, p);
+  }
+  return r;
+}
 // a^{-1} = a^{p-2} (p prime)
 inline fe invmod(const fe& a, const fe& p) {
   fe e;

@@ -164,6 +164,17 @@ int stk_merkle_finish(stk_ctx* c, uint8_t* d_nodes, uint64_t np, uint8_t* h_root
   return STK_OK;
 }
 
+int stk_merkle_paths_dev(stk_ctx* c, const fe* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
+                         const uint8_t* d_nodes, const uint64_t* d_idx, uint64_t k, uint32_t* d_out, uint64_t rec_bytes) {
+  if (!k) return STK_OK;
+  const uint64_t np = 4 * (n / 4);
+  if (np == 0 || (np & (np - 1))) return stk_fail(c, STK_EUNSUPPORTED, "branch extraction needs a power-of-two tree");
+  merkle_paths_cols_kernel<<<(unsigned)k, 128, 0, c->stream>>>(d_cols, np, (uint32_t)ncols, col_stride,
+                                                               (const uint32_t*)d_nodes, d_idx, d_out, rec_bytes / 4);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
 STK_API int stk_merkle_commit(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
                               uint8_t* d_nodes, uint8_t* h_root) {
   if (!c || !d_cols || !d_nodes || ncols == 0) return STK_EINVAL;

@@ -306,3 +306,62 @@ STK_API int stk_lincomb(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uint64_t
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }
+
+// get_computational_trace (starks/air.py:31-52) + the witness transposition of AIR.generate_witness
+// (:124): state[i+1][j] = step_poly_j(state[i]).  The recurrence is sequential by nature (one
+// 256-bit dependency chain of `steps` links), so it runs on one host core in the Montgomery
+// domain (hostmath.h) and writes witness[dim][step] in the ABI element layout -- pinned memory
+// from stk_host_alloc makes the following upload a single DMA.  Same monomial encoding as
+// stk_constraint_eval.
+STK_API int stk_trace_generate(stk_ctx* c, const uint32_t* h_inp, uint64_t steps, uint64_t width,
+                               const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs, const uint8_t* h_mono_exps,
+                               uint64_t nmono, uint32_t* h_witness) {
+  if (!c || !h_inp || !h_witness || steps == 0 || (nmono && (!h_mono_out || !h_mono_coeffs || !h_mono_exps)))
+    return STK_EINVAL;
+  if (width == 0 || width > 12) return stk_fail(c, STK_EUNSUPPORTED, "state width must be in 1..12");
+  typedef unsigned __int128 u128;
+  const host::HostMont& H = host::host_mont(c->p);
+  struct M64 { uint64_t v[4]; };
+  auto addm = [&](const M64& a, const M64& b) {
+    M64 r;
+    u128 cy = 0;
+    for (int i = 0; i < 4; ++i) { cy += (u128)a.v[i] + b.v[i]; r.v[i] = (uint64_t)cy; cy >>= 64; }
+    bool ge = cy != 0;
+    if (!ge) {
+      ge = true;
+      for (int i = 3; i >= 0; --i) { if (r.v[i] > H.m[i]) break; if (r.v[i] < H.m[i]) { ge = false; break; } }
+    }
+    if (ge) {
+      uint64_t bw = 0;
+      for (int i = 0; i < 4; ++i) { u128 d = (u128)r.v[i] - H.m[i] - bw; r.v[i] = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1; }
+    }
+    return r;
+  };
+  auto to_mont = [&](const fe& x) { M64 a, r; host::to64(x, a.v); host::mont64(H, a.v, H.r2, r.v); return r; };
+  const uint64_t one_plain[4] = {1, 0, 0, 0};
+  std::vector<M64> coef(nmono ? nmono : 1);
+  for (uint64_t m = 0; m < nmono; ++m) {
+    if (h_mono_out[m] >= width) return stk_fail(c, STK_EINVAL, "monomial output index out of range");
+    coef[m] = to_mont(host::reduce(stk_load_fe(h_mono_coeffs + 8 * m), c->p));
+  }
+  M64 st[12], nx[12];
+  for (uint64_t k = 0; k < width; ++k) st[k] = to_mont(host::reduce(stk_load_fe(h_inp + 8 * k), c->p));
+  for (uint64_t i = 0; i < steps; ++i) {
+    for (uint64_t k = 0; k < width; ++k) {  // leave the Montgomery domain on the way out
+      uint64_t plain[4];
+      host::mont64(H, st[k].v, one_plain, plain);
+      fe o = host::from64(plain);
+      memcpy(h_witness + (k * steps + i) * 8, o.v, 32);
+    }
+    if (i + 1 == steps) break;
+    for (uint64_t j = 0; j < width; ++j) memset(nx[j].v, 0, 32);
+    for (uint64_t m = 0; m < nmono; ++m) {
+      M64 t = coef[m];
+      for (uint64_t k = 0; k < width; ++k)
+        for (uint32_t e = 0; e < h_mono_exps[width * m + k]; ++e) host::mont64(H, t.v, st[k].v, t.v);
+      nx[h_mono_out[m]] = addm(nx[h_mono_out[m]], t);
+    }
+    for (uint64_t j = 0; j < width; ++j) st[j] = nx[j];
+  }
+  return STK_OK;
+}

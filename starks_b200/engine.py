@@ -246,6 +246,38 @@ class Engine:
     self._check(self.lib.stk_fri_fold4(self.ctx, d_vals, n, _u32(int_to_limbs(int(root) % self.p)),
                                        _u32(int_to_limbs(int(special_x))), d_out))
 
+  def fri_prove(self, d_vals, n, d_nodes, root_bytes, root, maxdeg_plus_1, exclude_multiples_of, security):
+    """stk_fri_prove -> the proof list of generate_proximity_proof (starks/fri.py:189-266):
+    [[root2, [[branch(m2,y), branch(m,y), branch(m,y+q), branch(m,y+2q), branch(m,y+3q)], ...]], ...,
+    [final values as 32-byte big-endian]]."""
+    layers, nn, md, k, total = [], n, maxdeg_plus_1, security, 0
+    while md > 16:
+      q = nn // 4
+      d1, d2 = nn.bit_length() - 1, q.bit_length() - 1
+      layers.append((k, d1, d2))
+      total += 32 + k * (64 + 32 * (d2 - 1)) + 4 * k * (64 + 32 * (d1 - 1))
+      nn, md, k = q, md // 4, 40
+    total += 32 * nn
+    out = np.empty(total, dtype=np.uint8)
+    need = ctypes.c_uint64(0)
+    rb = (ctypes.c_uint8 * 32).from_buffer_copy(root_bytes) if d_nodes else None
+    self._check(self.lib.stk_fri_prove(self.ctx, d_vals, n, d_nodes or None, rb, _u32(int_to_limbs(int(root) % self.p)),
+                                       maxdeg_plus_1, exclude_multiples_of, security, out.ctypes.data, total,
+                                       ctypes.byref(need)))
+    assert need.value == total, (need.value, total)
+    buf, off, proof = out.tobytes(), 0, []
+    for k, d1, d2 in layers:
+      root2 = buf[off:off + 32]
+      off += 32
+      r2, r1 = 64 + 32 * (d2 - 1), 64 + 32 * (d1 - 1)
+      col = [list(t) for t in _path_struct(32, d2).iter_unpack(buf[off:off + k * r2])]
+      off += k * r2
+      rows = [list(t) for t in _path_struct(32, d1).iter_unpack(buf[off:off + 4 * k * r1])]
+      off += 4 * k * r1
+      proof.append([root2, [[col[i]] + rows[4 * i:4 * i + 4] for i in range(k)]])
+    proof.append(list(struct.unpack("32s" * nn, buf[off:off + 32 * nn])))
+    return proof
+
   def microbench(self, which, iters):
     ms, ops = ctypes.c_float(), ctypes.c_double()
     self._check(self.lib.stk_microbench(self.ctx, which, iters, ctypes.byref(ms), ctypes.byref(ops)))

@@ -50,7 +50,7 @@ class SmoothSubgroupFRI(object):
     layer = DeviceLayer(eng, d_vals.ptr, n, owner=[d_in, d_vals])
     return self.prove_from_device(layer, root, maxdeg_plus_1, exclude_multiples_of, fri_spot_check_security_factor)
 
-  def prove_from_device(self, layer, root, maxdeg_plus_1, exclude_multiples_of=0, security=40):
+  def prove_from_device(self, layer, root, maxdeg_plus_1, exclude_multiples_of=0, security=40, use_driver=True):
     """Same proof, starting from evaluations already on the device (and optionally their
     tree, as STARK.mk_proof has just built it for l_evaluations)."""
     eng = layer.eng
@@ -58,6 +58,17 @@ class SmoothSubgroupFRI(object):
     proof = []
     keep = list(layer.owner or [])
     d_vals, n, d_nodes, m_root = layer.d_vals, layer.n, layer.d_nodes, layer.root
+    nn, md = n, maxdeg_plus_1
+    fits = use_driver and n & (n - 1) == 0 and maxdeg_plus_1 > 16 and exclude_multiples_of != 1
+    while fits and md > 16:
+      fits, nn, md = nn >= 16 and nn // 4 < 2**24, nn // 4, md // 4
+    if fits:
+      # the whole commit phase in one library call (stk_fri_prove): same kernels as the loop
+      # below, one host synchronisation per layer and one download of the opened branches
+      proof = eng.fri_prove(d_vals, n, d_nodes, m_root, root, maxdeg_plus_1, exclude_multiples_of, security)
+      for b in keep:
+        b.free()
+      return proof
     while True:
       if maxdeg_plus_1 <= 16:                                            # :212-214
         vals = _download(eng, d_vals, n)

@@ -208,3 +208,30 @@ def test_fused_leaf_hash_matches_separate_commit(eng, oracle, monkeypatch):
       _, want_nodes = oracle.merkelize_bytes(leaves, 4)
       assert got["1"][0] == want_nodes[1].tobytes()
     d_tr.free(); d_ev.free()
+
+
+def test_fri_driver_matches_layer_loop(eng, oracle):
+  """stk_fri_prove (whole commit phase in the library) must produce the same proof object as the
+  per-layer Python loop over the same kernels (starks/fri.py:189-266)."""
+  from starks_b200.fri import FRI, DeviceLayer
+  from starks_b200.modp import IntegersModP
+  fri = FRI(IntegersModP(P), engine=eng)
+  rng = np.random.default_rng(31)
+  for logn, maxdeg, excl, sec, with_tree in ((6, 17, 0, 40, False), (10, 128, 8, 40, True), (13, 1024, 8, 10, False),
+                                             (16, 8192, 0, 40, True), (12, 64, 4, 3, False)):
+    n = 1 << logn
+    w = pow(7, (P - 1) // n, P)
+    vals = rand_cols(rng, 1, n)[0]
+    d = eng.alloc(vals.nbytes).upload(vals)
+    nodes, root = None, None
+    if with_tree:
+      nodes = eng.alloc(32 * n)
+      root = eng.merkle_commit(d.ptr, n, 1, n, nodes.ptr)
+    mk = lambda: DeviceLayer(eng, d.ptr, n, nodes.ptr if nodes else None, root)
+    a = fri.prove_from_device(mk(), w, maxdeg, exclude_multiples_of=excl, security=sec, use_driver=True)
+    b = fri.prove_from_device(mk(), w, maxdeg, exclude_multiples_of=excl, security=sec, use_driver=False)
+    assert a == b, (logn, maxdeg, excl, sec)
+    assert len(a) >= 2 and len(a[0][1]) == sec
+    d.free()
+    if nodes:
+      nodes.free()
