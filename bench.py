@@ -30,9 +30,9 @@ LOGN = 20
 N = 1 << LOGN
 INT_OPS_PER_BUTTERFLY = 264       # SURVEY.md 8(d), frozen
 BYTES_PER_ELEM = 64               # read once + write once
-# measured once per change with ncu (profiles/r01_ncu_ntt_pass_summary.txt): the two passes of
-# one step move 4.43 GB and 4.24 GB; each pass reads and writes the whole 2 GiB batch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 4.34e9
+# measured once per change with ncu (profiles/r01b_ncu_ntt_pass_summary.txt): the two passes of
+# one step move 4.45 GB and 4.25 GB; each pass reads and writes the whole 2 GiB batch
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 4.35e9
 
 
 def peaks():
@@ -393,11 +393,11 @@ def main():
         "clocks": clocks,
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_ntt_pass_summary.txt",
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_ncu_ntt_pass_summary.txt",
                      "alg_bytes_per_launch": alg_bytes / launches_per_step, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                      "kernel": "ntt_pass_kernel<StarkField>", "launches_per_step": launches_per_step,
                      "alg_bytes_per_step": alg_bytes,
-                     "note": "the kernel is bound by the integer pipes, not HBM (256-bit modular butterflies: ~41 int32 op per byte against a machine balance of ~4.7): int_roofline below is the binding one; DRAM is 11.7 % busy in ncu"},
+                     "note": "the kernel is bound by the integer pipes, not HBM (256-bit modular butterflies: ~41 int32 op per byte against a machine balance of ~4.7): int_roofline below is the binding one; DRAM is 12 % busy in ncu"},
         "int_roofline": {"bound": "int32 pipes", "alg_int32_ops_per_step": int_ops,
                          "achieved_gops": int_ops / (ms_step * 1e-3) / 1e9,
                          "peak_gops": mb.get("imad_iadd3_mixed_gops"), "peak_source": "K0 microbenchmark (IMAD+IADD3 dual issue), same run",
