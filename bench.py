@@ -351,6 +351,7 @@ def main():
       eng.ntt_host(host_in.array, N, w, out=host_out.array)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    barrier()  # all ranks copy at once, like the e2e steps: the host side is shared
     pcie_duplex = pcie_duplex_ceiling(torch, local)
   if world > 1:
     t = torch.tensor([ms, e2e_s or 0.0], dtype=torch.float64, device="cuda:%d" % local)
