@@ -47,6 +47,15 @@ struct NttPass {
   // non-zero element per group and becomes x[m] = x[0] * w^(J*rev3(m)).  zbit = log2 of the
   // padded input length (32 disables the shortcut).
   int zbit;
+  // LDE by cosets (zero-padded input, n_in <= N/8): the transform of order 8*2^n over <w> is run as
+  // 8 independent transforms of order 2^n over <w^8>, one per residue r of the OUTPUT index:
+  // out[8K + r] = sum_j (c_j * w^(r*j)) * (w^8)^(jK).  Virtual column vc = 8*col + r: real column
+  // vc >> cshift for the first pass's input and the final pass's output, residue r = vc mod 8; the
+  // first round multiplies c_j by W[(r*j) << cs_shift] (ZS instantiations only) and the final store
+  // goes to index (K << cshift) | r.  cshift = 0 everywhere else.
+  int cshift;
+  int cs_shift;
+  int in_virtual;  // this pass reads the virtual columns (not the first pass of a coset transform)
   int tw_shift;  // the table is a longer one: entry e lives at W[e << tw_shift]
   int n_tw;
   int j_shift;
@@ -108,12 +117,23 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
     const bool col_ok = col < A.batch;
     fe x[M];
     if (first) {
-      const fe* src = A.in + (unsigned long long)col * A.in_col_stride;
+      const uint32_t icol = A.in_virtual ? col : (col >> A.cshift);
+      const fe* src = A.in + (unsigned long long)icol * A.in_col_stride;
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         uint32_t J = J0 + ((uint32_t)m << gshift);
         uint32_t Jm = A.in_rot ? (((J & ((1u << A.in_rot) - 1u)) << (A.n - A.in_rot)) | (J >> A.in_rot)) : J;
         x[m] = (col_ok && J < A.n_in) ? fe_load(src + Jm) : fe_zero();
+      }
+      if (ZS && A.cshift && !A.in_virtual) {  // coset scaling c_j * w^(r*j); r = 0 needs none
+        const uint32_t r = col & ((1u << A.cshift) - 1u);
+        if (r) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const uint32_t J = J0 + ((uint32_t)m << gshift);
+            x[m] = f.mul_tw(x[m], fe_load_ro(A.W + ((unsigned long long)(r * J) << A.cs_shift)));
+          }
+        }
       }
     } else {
 #pragma unroll
@@ -164,11 +184,13 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
     }  // butterfly levels
     if (last && !A.peer_on) {
       if (col_ok) {
-        fe* dst = A.out + (unsigned long long)col * A.out_col_stride;
+        const bool ovirt = !A.final_pass || !A.cshift;  // non-final passes keep virtual columns apart
+        fe* dst = A.out + (unsigned long long)(ovirt ? col : (col >> A.cshift)) * A.out_col_stride;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
           uint32_t J = J0 + ((uint32_t)m << gshift);
           uint32_t K = A.final_pass ? ((__brev((J << A.j_shift) | A.j_or) >> (32 - A.n_tw)) >> A.out_shift) : J;
+          if (!ovirt) K = (K << A.cshift) | (col & ((1u << A.cshift) - 1u));
           fe v = x[m];
           if (A.do_scale) v = f.mul_tw(v, A.scale);
           fe_store(dst + K, v);

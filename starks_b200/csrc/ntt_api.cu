@@ -282,8 +282,11 @@ template <class F>
 static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
   if constexpr (F::kMontgomery) return stk_launch_pass_mont(c, s, P);
   else if (P.hash_on) return stk_launch_pass_stark_hash(c, s, P);
-  else if (P.logT > 10) return P.zbit < 32 ? stk_launch_pass_stark_t11_zs(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
-  else return P.zbit < 32 ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
+  else {
+  const bool zs = P.zbit < 32 || (P.cshift && !P.in_virtual);  // expansion round / coset scaling on load
+  if (P.logT > 10) return zs ? stk_launch_pass_stark_t11_zs(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
+  else return zs ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
+  }
 }
 
 // direct DFT for orders that are not a power of two >= 8 (_simple_ft, starks/fft.py:287-300)
@@ -374,6 +377,39 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   }
   int logn = ilog2_u64(n);
   std::vector<NttPass> plan;
+  // Zero-padded forward transform (LDE, n_in <= N/8): eight coset transforms of order N/8 over
+  // <w^8> as 8*batch virtual columns (ntt.cuh, cshift) -- the sub-transform's passes split its
+  // own bits evenly (2^18: 9+9, 2^20: 10+10) instead of the long transform's (11+10, 8+8+7).
+  if (c->is_stark && !inverse && !peer && !hash_nodes && n_in > 0 && n_in * 8 <= n && logn >= 6 &&
+      (const void*)d_in != (const void*)d_out && env_int("STK_LDE_COSET", 1)) {
+    const int logns = logn - 3;
+    const uint64_t ns = n >> 3, vb = batch * 8;
+    STK_TRY(build_plan(logns, vb, plan, ntt_max_radix()));
+    if (vb <= 0x7fffffffull && (plan.size() == 1 || vb <= 65535)) {
+      fe* tmpc = nullptr;
+      if (plan.size() > 1) {
+        void* t;
+        STK_TRY(stk_scratch(c, scratch_slot, batch * n * sizeof(fe), &t));
+        tmpc = (fe*)t;
+      }
+      for (size_t i = 0; i < plan.size(); ++i) {
+        NttPass& P = plan[i];
+        P.batch = (uint32_t)vb;
+        P.W = W;
+        P.cs_shift = ilog2_u64(wstride);
+        P.tw_shift = P.cs_shift + 3;
+        P.cshift = 3;
+        P.in_virtual = i > 0;
+        P.zbit = 32;
+        if (i == 0) { P.in = d_in; P.in_col_stride = in_stride; P.n_in = (uint32_t)n_in; }
+        else { P.in = tmpc; P.in_col_stride = ns; P.n_in = (uint32_t)ns; }
+        if (P.final_pass) { P.out = d_out; P.out_col_stride = out_stride; }
+        else { P.out = tmpc; P.out_col_stride = ns; }
+        STK_TRY(launch_pass<StarkField>(c, s, P, StarkField()));
+      }
+      return STK_OK;
+    }
+  }
   STK_TRY(build_plan(logn, batch, plan, c->is_stark ? ntt_max_radix() : 2));
   fe* tmp = nullptr;
   if (peer && (plan.size() < 2 || logn - 2 - peer->g < plan.back().logC))

@@ -37,7 +37,15 @@ def lde(logs, cols, ext=8):
     tr = torch.randint(0, 2**31-1, (cols, steps, 8), dtype=torch.int32, device='cuda')
     ev = torch.empty((cols, N, 8), dtype=torch.int32, device='cuda')
     return timeit(lambda: eng.lde(tr.data_ptr(), steps, steps, ext, cols, g2, ev.data_ptr(), N))
-cases = [('ntt20x64', lambda: ntt(20, 64)), ('intt20x64', lambda: ntt(20, 64, True)), ('ntt24x4', lambda: ntt(24, 4)),
+def zp(logn, cols):
+    """zero-padded forward transform: n_in = N/8 coefficients per column (the proof's batched evaluation)"""
+    N = 1 << logn; nin = N >> 3
+    w = pow(7, (P-1)//N, P)
+    bufs.clear(); torch.cuda.empty_cache()
+    d_in = torch.randint(0, 2**31-1, (cols, nin, 8), dtype=torch.int32, device='cuda')
+    d_out = torch.empty((cols, N, 8), dtype=torch.int32, device='cuda')
+    return timeit(lambda: eng.ntt(d_in.data_ptr(), nin, nin, d_out.data_ptr(), N, N, cols, w))
+cases = [('zp23x6', lambda: zp(23, 6)), ('zp21x64', lambda: zp(21, 64)), ('zp16x512', lambda: zp(16, 512)), ('ntt20x64', lambda: ntt(20, 64)), ('intt20x64', lambda: ntt(20, 64, True)), ('ntt24x4', lambda: ntt(24, 4)),
          ('ntt16x1024', lambda: ntt(16, 1024)), ('ntt12x16384', lambda: ntt(12, 16384)), ('ntt23x6', lambda: ntt(23, 6)),
          ('lde18x64', lambda: lde(18, 64)), ('lde20x2', lambda: lde(20, 2))]
 if os.environ.get('KNOB_CASES'):
