@@ -22,6 +22,9 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, uint32_t s
     acc64[i] = ((unsigned long long)a[i] << 32) | b[i];
   }
   uint32_t k = seed | 1u;
+  double da[kIlp], dk = 1.0 + (double)(seed & 7u) * 0x1p-40, dc = 0x1p-30;
+#pragma unroll
+  for (int i = 0; i < kIlp; ++i) da[i] = 1.0 + (double)i * 0x1p-20 + (double)(t & 255u) * 0x1p-30;
   for (uint64_t it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -63,6 +66,14 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, uint32_t s
         } else if (WHICH == 7) {  // IMAD + IADD3 on independent chains
           asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(a[i]) : "r"(k));
           asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(k));
+        } else if (WHICH == 11) {  // DFMA (FP64 pipe)
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(da[i]) : "d"(dk), "d"(dc));
+        } else if (WHICH == 12) {  // DFMA + IMAD.WIDE on independent chains
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(da[i]) : "d"(dk), "d"(dc));
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc64[i]) : "r"((uint32_t)acc64[i]), "r"(k));
+        } else if (WHICH == 13) {  // DFMA + two IADD3 on independent chains
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(da[i]) : "d"(dk), "d"(dc));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(k));
         } else if (WHICH == 8) {  // IMAD.WIDE + IADD3 on independent chains
           asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc64[i]) : "r"((uint32_t)acc64[i]), "r"(k));
           asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(k));
@@ -72,7 +83,9 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, uint32_t s
   }
   uint32_t acc = 0;
 #pragma unroll
-  for (int i = 0; i < kIlp; ++i) acc ^= a[i] ^ b[i] ^ (uint32_t)acc64[i] ^ (uint32_t)(acc64[i] >> 32);
+  for (int i = 0; i < kIlp; ++i)
+    acc ^= a[i] ^ b[i] ^ (uint32_t)acc64[i] ^ (uint32_t)(acc64[i] >> 32) ^ (uint32_t)__double2loint(da[i]) ^
+           (uint32_t)__double2hiint(da[i]);
   out[t] = acc;
 }
 
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t* out, uint32_t s
 __host__ double ops_per_iter(int which) {
   switch (which) {
     case 4: return 4.0 * kIlp * 3;   // IADD3 + LOP3 + SHF
-    case 7: case 8: return 4.0 * kIlp * 2;
+    case 7: case 8: case 12: case 13: return 4.0 * kIlp * 2;
     case 9: return 4.0 * 2 * kIlp;   // two 8-limb add chains
     case 10: return 4.0 * 8;         // eight wide multiply-adds
     default: return 4.0 * kIlp;
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(256) field_kernel(fe* out, const fe* in, uint6
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int stk_microbench(stk_ctx* c, int which, uint64_t iters, float* ms, double* ops) {
-  if (!c || !ms || !ops || which < 0 || which > 10) return STK_EINVAL;
+  if (!c || !ms || !ops || which < 0 || which > 13) return STK_EINVAL;
   const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
   void* buf;
   STK_TRY(stk_scratch(c, 2, (uint64_t)blocks * threads * sizeof(fe) + 1024 * sizeof(fe), &buf));
@@ -130,7 +143,7 @@ extern "C" __attribute__((visibility("default"))) int stk_microbench(stk_ctx* c,
     STK_CUDA(c, cudaEventRecord(e0, c->stream));
     switch (which) {
 #define IPK(W) case W: int_pipe_kernel<W><<<blocks, threads, 0, c->stream>>>((uint32_t*)out, 12345u, iters); break;
-      IPK(0) IPK(1) IPK(2) IPK(3) IPK(4) IPK(7) IPK(8) IPK(9) IPK(10)
+      IPK(0) IPK(1) IPK(2) IPK(3) IPK(4) IPK(7) IPK(8) IPK(9) IPK(10) IPK(11) IPK(12) IPK(13)
 #undef IPK
       case 5:
         if (c->is_stark) field_kernel<StarkField, 5><<<blocks, threads, 0, c->stream>>>(out, in, iters, StarkField());

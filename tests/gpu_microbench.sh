@@ -7,8 +7,9 @@ import sys; sys.path.insert(0, '.')
 from starks_b200 import Engine
 e = Engine(0)
 names = {0:"IMAD",1:"IMAD.WIDE+IADD3+IADD3.X (split)",2:"IADD3",3:"IMAD.HI(+MOV)",4:"IADD3+LOP3+SHF",5:"field_mul",6:"butterfly",
-         7:"IMAD+IADD3 indep",8:"IMAD.WIDE+2.5 IADD3",9:"IADD3.X carry chain",10:"IMAD.WIDE.X rows"}
-for w in range(11):
+         7:"IMAD+IADD3 indep",8:"IMAD.WIDE+2.5 IADD3",9:"IADD3.X carry chain",10:"IMAD.WIDE.X rows",
+         11:"DFMA (fp64 pipe)",12:"DFMA + IMAD.WIDE indep",13:"DFMA + 2 IADD3 indep"}
+for w in range(14):
     iters = 20000 if w not in (5,6) else 2000
     best = None
     for rep in range(3):
