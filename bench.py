@@ -227,6 +227,9 @@ def extras(eng, torch, stream, local):
   for _ in range(3):
     proof = S.mk_proof(witness, [(0, 0, 0), (0, 1, 1)])
   out["stark_proof_s_fib_2^20_steps_x8"] = (time.perf_counter() - t0) / 3
+  t0 = time.perf_counter()
+  assert S.verify_proof(proof, witness, [(0, 0, 0), (0, 1, 1)])
+  out["stark_verify_s_fib_2^20_steps_x8"] = time.perf_counter() - t0
   out["stark_proof_fri_layers"] = len(proof[3])
   out["stark_proof_phases_ms"] = {k: round(v, 2) for k, v in S.timings.items() if k.endswith("_ms")}
   return out

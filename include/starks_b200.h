@@ -147,6 +147,12 @@ int stk_merkle_commit_raw(stk_ctx* ctx, const uint8_t* d_leaves, uint64_t n, uin
 int stk_merkle_paths(stk_ctx* ctx, const uint32_t* d_cols, uint64_t n, uint64_t ncols, uint64_t col_stride,
                      const uint8_t* d_nodes, const uint64_t* h_indices, uint64_t k, uint8_t* h_out,
                      uint64_t rec_bytes);
+/* verify_branch (starks/merkle_tree.py:71-86) for k branches of ONE tree of n leaves (a power
+ * of two, leaves of leaf_len bytes, a multiple of 32): h_records holds k stk_merkle_paths
+ * records (leaf | sibling leaf | sibling nodes), h_ok[r] = 1 when branch r hashes up to root. */
+int stk_verify_branches(stk_ctx* ctx, const uint8_t root[32], uint64_t n, uint64_t leaf_len,
+                        const uint64_t* h_indices, uint64_t k, const uint8_t* h_records, uint64_t rec_bytes,
+                        uint8_t* h_ok);
 
 /* ---- FRI ------------------------------------------------------------------------- */
 /* The `column` of one FRI layer (starks/fri.py:236-242; multi_interp_4,

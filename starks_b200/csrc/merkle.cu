@@ -138,6 +138,49 @@ __global__ void __launch_bounds__(128) merkle_paths_cols_kernel(const fe* __rest
   }
 }
 
+// verify_branch (starks/merkle_tree.py:71-86) for many branches of one tree: one thread per
+// record (own leaf | sibling leaf | sibling nodes up to the root), ok[r] = recomputed root == root.
+__global__ void __launch_bounds__(128) verify_branches_kernel(const uint32_t* __restrict__ rec, uint64_t rec_words,
+                                                               const uint64_t* __restrict__ idx, uint64_t k, uint64_t n,
+                                                               uint32_t leaf_words, uint32_t depth,
+                                                               const uint32_t* __restrict__ root, uint8_t* __restrict__ ok) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= k) return;
+  const uint32_t* R = rec + r * rec_words;
+  const uint64_t x = idx[r], q = n >> 2;
+  uint64_t index = x / q + 4 * (x % q) + n;   // get_index_in_permuted + leaf offset (:26-33, :73-78)
+  uint32_t h[8];
+  b2s_init(h);
+  const uint32_t* first = (index & 1) ? R + leaf_words : R;   // odd: sibling || own
+  const uint32_t* second = (index & 1) ? R : R + leaf_words;
+  const uint32_t total = 2 * leaf_words;  // a multiple of 16 words (leaves are 32*ncols bytes)
+  for (uint32_t w0 = 0; w0 < total; w0 += 16) {
+    uint32_t m[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t w = w0 + j;
+      m[j] = w < leaf_words ? first[w] : second[w - leaf_words];
+    }
+    b2s_compress(h, m, 4u * (w0 + 16), w0 + 16 == total);
+  }
+  index >>= 1;
+  for (uint32_t d = 0; d + 1 < depth; ++d, index >>= 1) {
+    const uint32_t* sib = R + 2 * leaf_words + 8 * d;
+    uint32_t m[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m[j] = (index & 1) ? sib[j] : h[j];
+      m[8 + j] = (index & 1) ? h[j] : sib[j];
+    }
+    b2s_init(h);
+    b2s_compress(h, m, 64u, true);
+  }
+  uint32_t diff = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) diff |= h[j] ^ root[j];
+  ok[r] = diff == 0;
+}
+
 // Power-of-two trees: nodes [1, np/2) have node children; levels go bottom-up, the last
 // (at most 1024-node) levels run inside one CTA.
 int reduce_levels(stk_ctx* c, uint32_t* nodes, uint64_t np) {
@@ -252,6 +295,40 @@ STK_API int stk_merkle_paths(stk_ctx* c, const uint32_t* d_cols, uint64_t n, uin
                                                                (const uint32_t*)d_nodes, d_idx, d_out, rec_bytes / 4);
   STK_CUDA(c, cudaGetLastError());
   STK_CUDA(c, cudaMemcpyAsync(h_out, d_out, k * rec_bytes, cudaMemcpyDeviceToHost, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return STK_OK;
+}
+
+// verify_branch (starks/merkle_tree.py:71-86) for k branches of ONE tree of n leaves (a power of
+// two) whose leaves are leaf_len bytes (a multiple of 32): records as stk_merkle_paths returns
+// them.  h_ok[r] = 1 when branch r hashes up to `root`.
+STK_API int stk_verify_branches(stk_ctx* c, const uint8_t root[32], uint64_t n, uint64_t leaf_len,
+                                const uint64_t* h_indices, uint64_t k, const uint8_t* h_records, uint64_t rec_bytes,
+                                uint8_t* h_ok) {
+  if (!c || !root || !h_indices || !h_records || !h_ok) return STK_EINVAL;
+  if (!k) return STK_OK;
+  if (n < 4 || (n & (n - 1))) return stk_fail(c, STK_EUNSUPPORTED, "branch verification needs a power-of-two tree");
+  if (leaf_len == 0 || (leaf_len & 31)) return stk_fail(c, STK_EINVAL, "leaf length must be a multiple of 32 bytes");
+  uint32_t depth = 0;
+  while ((1ull << depth) < n) ++depth;
+  if (rec_bytes != 2 * leaf_len + 32ull * (depth - 1)) return stk_fail(c, STK_EINVAL, "record size does not match the tree depth");
+  for (uint64_t i = 0; i < k; ++i)
+    if (h_indices[i] >= n) return stk_fail(c, STK_EINDEX, "branch index out of range");
+  const uint64_t rb = k * rec_bytes, ib = k * 8;
+  void* buf;
+  STK_TRY(stk_scratch(c, 2, rb + ib + 32 + k + 64, &buf));
+  uint8_t* base = (uint8_t*)buf;
+  uint32_t* d_rec = (uint32_t*)base;
+  uint64_t* d_idx = (uint64_t*)(base + ((rb + 7) & ~7ull));
+  uint32_t* d_root = (uint32_t*)((uint8_t*)d_idx + ib);
+  uint8_t* d_ok = (uint8_t*)d_root + 32;
+  STK_CUDA(c, cudaMemcpyAsync(d_rec, h_records, rb, cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaMemcpyAsync(d_idx, h_indices, ib, cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaMemcpyAsync(d_root, root, 32, cudaMemcpyHostToDevice, c->stream));
+  verify_branches_kernel<<<(unsigned)((k + 127) / 128), 128, 0, c->stream>>>(d_rec, rec_bytes / 4, d_idx, k, n,
+                                                                            (uint32_t)(leaf_len / 4), depth, d_root, d_ok);
+  STK_CUDA(c, cudaGetLastError());
+  STK_CUDA(c, cudaMemcpyAsync(h_ok, d_ok, k, cudaMemcpyDeviceToHost, c->stream));
   STK_CUDA(c, cudaStreamSynchronize(c->stream));
   return STK_OK;
 }

@@ -242,6 +242,28 @@ class Engine:
     res = [list(t) for t in S.iter_unpack(out.tobytes())]
     return res
 
+  def verify_branches(self, root, indices, branches):
+    """verify_branch (starks/merkle_tree.py:71-86) for many branches of one tree in one kernel.
+    Returns the leaves (proof[0] of every branch); raises AssertionError like the reference
+    when a branch does not hash up to `root`."""
+    k = len(indices)
+    if k == 0:
+      return []
+    depth = len(branches[0]) - 1
+    n = 1 << depth
+    L = len(branches[0][0])
+    rec = 2 * L + 32 * (depth - 1)
+    assert all(len(b) == depth + 1 for b in branches), "branches of one tree have one length"
+    buf = np.frombuffer(b"".join(b"".join(b) for b in branches), dtype=np.uint8)
+    assert buf.size == k * rec, "malformed branch"
+    idx = np.asarray(indices, dtype=np.uint64)
+    ok = np.zeros(k, dtype=np.uint8)
+    rb = (ctypes.c_uint8 * 32).from_buffer_copy(root)
+    self._check(self.lib.stk_verify_branches(self.ctx, rb, n, L, idx.ctypes.data, k, buf.ctypes.data, rec,
+                                             ok.ctypes.data))
+    assert ok.all(), "Merkle branch does not match the root"
+    return [b[0] for b in branches]
+
   def fri_fold4(self, d_vals, n, root, special_x, d_out):
     self._check(self.lib.stk_fri_fold4(self.ctx, d_vals, n, _u32(int_to_limbs(int(root) % self.p)),
                                        _u32(int_to_limbs(int(special_x))), d_out))

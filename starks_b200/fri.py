@@ -113,13 +113,32 @@ class SmoothSubgroupFRI(object):
       ys = get_pseudorandom_indices(root2, roudeg // 4, fri_spot_check_security_factor,
                                     exclude_multiples_of=exclude_multiples_of)
       quartic = [pow(root, roudeg * j // 4, p) for j in range(4)]        # :285-291
+      q = roudeg // 4
+      iota_inv, inv4 = quartic[3] if roudeg % 4 == 0 else None, pow(4, -1, p)
+      if self._engine is not None and q >= 4 and q & (q - 1) == 0:
+        # every branch of the layer re-hashed in two kernels (stk_verify_branches)
+        f_ = lambda b: int.from_bytes(b, "big")
+        rows_all = [f_(v) for v in self._engine.verify_branches(
+            merkle_root, [y + q * j for y in ys for j in range(4)], [br for i in range(len(ys)) for br in branches[i][1:]])]
+        cols_all = [f_(v) for v in self._engine.verify_branches(root2, ys, [branches[i][0] for i in range(len(ys))])]
+      else:
+        rows_all = cols_all = None
       for i, y in enumerate(ys):
         x1 = pow(root, y, p)
         xs = [quartic[j] * x1 % p for j in range(4)]
-        row = [verify_branch(merkle_root, y + (roudeg // 4) * j, br, output_as_int=True)
-               for j, br in zip(range(4), branches[i][1:])]
-        col = verify_branch(root2, y, branches[i][0], output_as_int=True)
-        assert _lagrange_eval(xs, row, special_x, p) == col % p           # :330-333
+        if rows_all is not None:
+          row, col = rows_all[4 * i:4 * i + 4], cols_all[i]
+        else:
+          row = [verify_branch(merkle_root, y + q * j, br, output_as_int=True)
+                 for j, br in zip(range(4), branches[i][1:])]
+          col = verify_branch(root2, y, branches[i][0], output_as_int=True)
+        if iota_inv is not None:
+          # the degree<4 interpolant through (x1*iota^j, row[j]) at special_x in closed form (what
+          # stk_fri_fold4 computes): no modular inverse -- x1^-1 = root^(roudeg - y)
+          t = special_x * pow(root, roudeg - y, p) % p
+          assert _fold4_eval(row, t, iota_inv, inv4, p) == col % p        # :330-333
+        else:
+          assert _lagrange_eval(xs, row, special_x, p) == col % p
       merkle_root = root2
       root = pow(root, 4, p)
       maxdeg_plus_1 //= 4
@@ -131,8 +150,10 @@ class SmoothSubgroupFRI(object):
     pts = [x for x in range(len(data)) if x % exclude_multiples_of] if exclude_multiples_of else list(range(len(data)))
     xs = [powers[x] for x in pts[:maxdeg_plus_1]]
     ys_ = [data[x] % p for x in pts[:maxdeg_plus_1]]
+    if len(pts) > maxdeg_plus_1:
+      ws = _interp_weights(xs, p)
     for x in pts[maxdeg_plus_1:]:                                        # :357-362
-      assert _lagrange_eval(xs, ys_, powers[x], p) == data[x] % p
+      assert _weighted_eval(xs, ws, ys_, powers[x], p) == data[x] % p
     return True
 
 
@@ -146,6 +167,50 @@ def _host_merkle_root(data):
   for i in range(n - 1, 0, -1):
     tree[i] = blake(tree[2 * i] + tree[2 * i + 1])
   return tree[1]
+
+
+def _fold4_eval(row, t, iota_inv, inv4, p):
+  """1/4 * sum_k t^k * sum_j row[j] * iota^(-jk): the value at special_x = t*x1 of the cubic through
+  (x1*iota^j, row[j]) -- multi_interp_4 + Polynomial.__call__ (starks/poly_utils.py:412-440) in
+  closed form; exact arithmetic, so equal to the interpolation route."""
+  v0, v1, v2, v3 = row
+  s02, d02, s13, d13 = v0 + v2, v0 - v2, v1 + v3, v1 - v3
+  m = d13 * iota_inv % p
+  c0, c1, c2, c3 = s02 + s13, d02 + m, s02 - s13, d02 - m
+  return (((c3 * t + c2) % p * t + c1) % p * t + c0) % p * inv4 % p
+
+
+def _interp_weights(xs, p):
+  """1 / prod_{j != i} (x_i - x_j) for every i, with one modular inversion (multi_inv,
+  starks/poly_utils.py:301-320)."""
+  dens = []
+  for i, xi in enumerate(xs):
+    d = 1
+    for j, xj in enumerate(xs):
+      if i != j:
+        d = d * (xi - xj) % p
+    dens.append(d)
+  pref = [1]
+  for d in dens:
+    pref.append(pref[-1] * d % p)
+  inv = pow(pref[-1], -1, p)
+  out = [0] * len(xs)
+  for i in range(len(xs) - 1, -1, -1):
+    out[i] = pref[i] * inv % p
+    inv = inv * dens[i] % p
+  return out
+
+
+def _weighted_eval(xs, ws, ys, x, p):
+  """Value at x of the interpolant through (xs, ys) given the weights above: sum_i y_i w_i
+  prod_{j != i} (x - x_j), the products by prefix / suffix (no inversion per point)."""
+  n = len(xs)
+  pre, suf = [1] * (n + 1), [1] * (n + 1)
+  for i in range(n):
+    pre[i + 1] = pre[i] * (x - xs[i]) % p
+  for i in range(n - 1, -1, -1):
+    suf[i] = suf[i + 1] * (x - xs[i]) % p
+  return sum(ys[i] * ws[i] % p * pre[i] % p * suf[i + 1] for i in range(n)) % p
 
 
 def _lagrange_eval(xs, ys, x, p):

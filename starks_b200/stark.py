@@ -231,8 +231,17 @@ class STARK(object):
     positions = get_pseudorandom_indices(l_root, self.precision, samples,
                                          exclude_multiples_of=self.extension_factor)
     ks = get_pseudorandom_ks(m_root, 4)
+    N, ext = self.precision, self.extension_factor
+    leaves = None
+    if self._engine is not None and N >= 4 and N & (N - 1) == 0:
+      # all 3 * samples branches re-hashed in two kernels (stk_verify_branches)
+      ml = self._engine.verify_branches(m_root, [x for pos in positions for x in (pos, (pos + ext) % N)],
+                                        [branches[3 * i + d] for i in range(len(positions)) for d in (0, 1)])
+      self._engine.verify_branches(l_root, positions, [branches[3 * i + 2] for i in range(len(positions))])
+      leaves = ml
     for i, pos in enumerate(positions):
-      self.verify_proof_at_position(witness, boundary, ks, proof, i, pos)
+      self.verify_proof_at_position(witness, boundary, ks, proof, i, pos,
+                                    checked_leaves=None if leaves is None else leaves[2 * i:2 * i + 2])
     return True
 
   def _step(self, j, state, p):
@@ -244,16 +253,20 @@ class STARK(object):
       acc = (acc + t) % p
     return acc
 
-  def verify_proof_at_position(self, witness, boundary, ks, proof, i, pos):
-    """stark.py:319-372."""
+  def verify_proof_at_position(self, witness, boundary, ks, proof, i, pos, checked_leaves=None):
+    """stark.py:319-372.  checked_leaves: the two m-tree leaves of this position when their
+    branches (and the l-tree branch) have already been verified in a batch."""
     p, width = self.field.p, self.width
     m_root, l_root, branches, fri_proof = proof
     G2, last = int(self.G2), int(self.last_step_position)
     x = pow(G2, pos, p)
-    leaf1 = unpack_merkle_leaf(verify_branch(m_root, pos, branches[i * 3]), width, 3)
-    leaf2 = unpack_merkle_leaf(verify_branch(m_root, (pos + self.extension_factor) % self.precision,
-                                             branches[i * 3 + 1]), width, 3)
-    verify_branch(l_root, pos, branches[i * 3 + 2], output_as_int=True)
+    if checked_leaves is not None:
+      leaf1, leaf2 = (unpack_merkle_leaf(v, width, 3) for v in checked_leaves)
+    else:
+      leaf1 = unpack_merkle_leaf(verify_branch(m_root, pos, branches[i * 3]), width, 3)
+      leaf2 = unpack_merkle_leaf(verify_branch(m_root, (pos + self.extension_factor) % self.precision,
+                                               branches[i * 3 + 1]), width, 3)
+      verify_branch(l_root, pos, branches[i * 3 + 2], output_as_int=True)
     f_ = lambda b: int.from_bytes(b, "big")   # field(bytes) does not reduce; values are canonical
     p_of_x = [f_(v) for v in leaf1[:width]]
     p_of_g1x = [f_(v) for v in leaf2[:width]]

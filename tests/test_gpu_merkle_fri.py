@@ -235,3 +235,30 @@ def test_fri_driver_matches_layer_loop(eng, oracle):
     d.free()
     if nodes:
       nodes.free()
+
+
+def test_batched_branch_verification(eng, oracle):
+  """stk_verify_branches == verify_branch (starks/merkle_tree.py:71-86) on every branch, and a
+  single flipped bit anywhere in a record is rejected."""
+  from starks_b200.merkle_tree import verify_branch
+  rng = np.random.default_rng(41)
+  for logn, ncols in ((2, 1), (5, 1), (10, 6), (14, 3), (12, 64)):
+    n = 1 << logn
+    cols = rand_cols(rng, ncols, n)
+    d = eng.alloc(cols.nbytes).upload(cols)
+    nodes = eng.alloc(32 * n)
+    root = eng.merkle_commit(d.ptr, n, ncols, n, nodes.ptr)
+    idx = sorted(set([0, 1, n // 4, n // 2, n - 1] + [int(x) for x in rng.integers(0, n, size=20)]))
+    brs = eng.merkle_paths(d.ptr, n, ncols, n, nodes.ptr, idx)
+    leaves = eng.verify_branches(root, idx, brs)
+    assert leaves == [verify_branch(root, i, b) for i, b in zip(idx, brs)]
+    for which in range(len(brs[0])):          # flip one bit in each part of one record
+      bad = [list(b) for b in brs]
+      part = bytearray(bad[len(idx) // 2][which])
+      part[len(part) // 2] ^= 0x10
+      bad[len(idx) // 2][which] = bytes(part)
+      with pytest.raises(AssertionError):
+        eng.verify_branches(root, idx, bad)
+    with pytest.raises(AssertionError):       # right branches, wrong positions
+      eng.verify_branches(root, idx[1:] + idx[:1], brs)
+    d.free(); nodes.free()

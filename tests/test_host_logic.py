@@ -159,3 +159,29 @@ def test_compression_mirror(oracle):
   e = g["stark_fib32_branches"]
   assert (len(cb), bin_length(cb), hashlib.blake2s(b"|".join(cb)).hexdigest()) == (e["n_objects"], e["bin_length"], e["digest"])
   assert decompress_branches(cb) == proof[2]
+
+
+def test_verifier_closed_forms_equal_lagrange_interpolation():
+  """The FRI verifier's fold check and final-layer check use closed forms; both must equal the
+  literal interpolation (multi_interp_4 / lagrange_interp + evaluation, starks/poly_utils.py:337-440)."""
+  import random
+  from starks_b200.fri import _fold4_eval, _interp_weights, _lagrange_eval, _weighted_eval
+  P = 2**256 - 351 * 2**32 + 1
+  rnd = random.Random(5)
+  for p, g, sizes in ((P, 7, (16, 4096, 1 << 23)), (97, 5, (4, 8, 32))):
+    for n in sizes:
+      root = pow(g, (p - 1) // n, p)
+      quartic = [pow(root, n * j // 4, p) for j in range(4)]
+      for _ in range(10):
+        y = rnd.randrange(n // 4)
+        x1 = pow(root, y, p)
+        xs = [quartic[j] * x1 % p for j in range(4)]
+        row = [rnd.randrange(p) for _ in range(4)]
+        sx = rnd.randrange(2**256)   # fri.py:229: the challenge is not reduced
+        t = sx * pow(root, n - y, p) % p
+        assert _fold4_eval(row, t, quartic[3], pow(4, -1, p), p) == _lagrange_eval(xs, row, sx, p)
+  xs = rnd.sample(range(1, 97), 16)
+  ys = [rnd.randrange(97) for _ in range(16)]
+  ws = _interp_weights(xs, 97)
+  for x in range(97):
+    assert _weighted_eval(xs, ws, ys, x, 97) == _lagrange_eval(xs, ys, x, 97)
