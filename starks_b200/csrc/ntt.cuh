@@ -99,7 +99,12 @@ __device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >
 // TRIV: the round's lowest level has global stride 1 (last round of the final pass of a whole
 // transform), so its exponent base is 0 and every mm == 0 twiddle is w^0 = 1: 7 of the 12
 // multiplies of a radix-8 round (3 of 4 for radix-4, the only one for radix-2) are skipped.
-template <class F, int R, bool ZS, bool TRIV>
+// ZS: 0 = plain pass; 1 = first pass of a zero-padded transform (expansion round or coset scaling
+// on load, real input column = virtual >> cshift; also the interleaved store, for single-pass
+// coset transforms); 2 = final pass of a coset transform (interleaved store only).  The plain
+// instantiation carries none of this: even a few extra integer instructions in its load / store
+// paths cost 2 % on the 64 x 2^20 transform (measured, tests/gpu_altlib.py).
+template <class F, int R, int ZS, bool TRIV>
 __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
                                           uint32_t Jcta, uint32_t col0, int a, bool first, bool last) {
   constexpr int M = 1 << R;
@@ -117,7 +122,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
     const bool col_ok = col < A.batch;
     fe x[M];
     if (first) {
-      const uint32_t icol = A.in_virtual ? col : (col >> A.cshift);
+      const uint32_t icol = (ZS == 1 && !A.in_virtual) ? (col >> A.cshift) : col;
       const fe* src = A.in + (unsigned long long)icol * A.in_col_stride;
 #pragma unroll
       for (int m = 0; m < M; ++m) {
@@ -125,7 +130,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
         uint32_t Jm = A.in_rot ? (((J & ((1u << A.in_rot) - 1u)) << (A.n - A.in_rot)) | (J >> A.in_rot)) : J;
         x[m] = (col_ok && J < A.n_in) ? fe_load(src + Jm) : fe_zero();
       }
-      if (ZS && A.cshift && !A.in_virtual) {  // coset scaling c_j * w^(r*j); r = 0 needs none
+      if (ZS == 1 && A.cshift && !A.in_virtual) {  // coset scaling c_j * w^(r*j); r = 0 needs none
         const uint32_t r = col & ((1u << A.cshift) - 1u);
         if (r) {
 #pragma unroll
@@ -145,7 +150,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
       }
     }
     // exponent of the last (smallest-half) level of this round
-    if (ZS && first && R == 3 && gshift >= A.zbit && gshift == A.n - 3) {
+    if (ZS == 1 && first && R == 3 && gshift >= A.zbit && gshift == A.n - 3) {
       // Zero-padded input (LDE, N = 8 * n_in): only x[0] is non-zero and the three levels of
       // this round reduce to x[m] = x[0] * w^(J0 * rev3(m)) -- seven multiplies, no add/sub,
       // instead of twelve butterflies on mostly-zero data.
@@ -184,7 +189,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t
     }  // butterfly levels
     if (last && !A.peer_on) {
       if (col_ok) {
-        const bool ovirt = !A.final_pass || !A.cshift;  // non-final passes keep virtual columns apart
+        const bool ovirt = ZS == 0 || !A.final_pass || !A.cshift;  // non-final passes keep virtual columns apart
         fe* dst = A.out + (unsigned long long)(ovirt ? col : (col >> A.cshift)) * A.out_col_stride;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -261,7 +266,7 @@ static __device__ __noinline__ void hash_tile_rows(const HashTile A, uint32_t xb
   }
 }
 
-template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, bool ZS = false, bool HASH = false>
+template <class F, int MAXR, int MAXT = (4096 >> MAXR), int MINB = 1, int ZS = 0, bool HASH = false>
 __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, const F f) {
   extern __shared__ __align__(16) uint32_t sm[];
   const uint32_t T = 1u << A.logT;

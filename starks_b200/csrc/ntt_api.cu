@@ -275,6 +275,8 @@ int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P);      //
 int stk_launch_pass_stark_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);   // + zero-skip levels
 int stk_launch_pass_stark_t11(stk_ctx* c, cudaStream_t s, const NttPass& P);     // 2048-element tiles
 int stk_launch_pass_stark_t11_zs(stk_ctx* c, cudaStream_t s, const NttPass& P);
+int stk_launch_pass_stark_cf(stk_ctx* c, cudaStream_t s, const NttPass& P);      // coset transform, final pass
+int stk_launch_pass_stark_t11_cf(stk_ctx* c, cudaStream_t s, const NttPass& P);
 int stk_launch_pass_mont(stk_ctx* c, cudaStream_t s, const NttPass& P);       // run-time modulus, radix-4
 int stk_launch_pass_stark_hash(stk_ctx* c, cudaStream_t s, const NttPass& P);  // final pass + Merkle bottom level
 
@@ -284,8 +286,11 @@ static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
   else if (P.hash_on) return stk_launch_pass_stark_hash(c, s, P);
   else {
   const bool zs = P.zbit < 32 || (P.cshift && !P.in_virtual);  // expansion round / coset scaling on load
-  if (P.logT > 10) return zs ? stk_launch_pass_stark_t11_zs(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
-  else return zs ? stk_launch_pass_stark_zs(c, s, P) : stk_launch_pass_stark(c, s, P);
+  const bool cf = !zs && P.cshift && P.final_pass;              // interleaved store only
+  if (P.logT > 10)
+    return zs ? stk_launch_pass_stark_t11_zs(c, s, P) : cf ? stk_launch_pass_stark_t11_cf(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
+  else
+    return zs ? stk_launch_pass_stark_zs(c, s, P) : cf ? stk_launch_pass_stark_cf(c, s, P) : stk_launch_pass_stark(c, s, P);
   }
 }
 

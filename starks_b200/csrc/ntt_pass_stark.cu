@@ -6,7 +6,7 @@
 
 using namespace stk;
 
-template <class F, int MAXR, int MAXT, int MINB, bool ZS>
+template <class F, int MAXR, int MAXT, int MINB, int ZS>
 static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
   static bool attr_done = false;
   if (!attr_done) {

@@ -1,5 +1,5 @@
-// ntt_pass_mont.cu -- one instantiation of the NTT pass kernel and its host-side launcher (split out of
-// ntt_api.cu so the heavy kernels compile in parallel).
+// ntt_pass_stark_t11_cf.cu -- final pass of a coset transform (interleaved store), 2048-element tiles; one instantiation per
+// translation unit so the heavy kernels compile in parallel (see ntt_pass_stark.cu).
 #include <algorithm>
 #include "ctx.h"
 #include "ntt.cuh"
@@ -11,11 +11,11 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   static bool attr_done = false;
   if (!attr_done) {
     STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 4 * MAXT));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 8 * MAXT));
     attr_done = true;
   }
   const uint32_t T = 1u << P.logT;
-  if ((1u << P.logT) > 4u * MAXT) return stk_fail(c, STK_EUNSUPPORTED, "tile larger than this instantiation");
+  if ((1u << P.logT) > 8u * MAXT) return stk_fail(c, STK_EUNSUPPORTED, "tile larger than this instantiation");
   unsigned threads = std::max(1u, T >> MAXR);
   uint64_t tiles = P.c_is_col ? 1 : ((1ull << P.n) >> P.logT);
   uint64_t cols = P.c_is_col ? ((P.batch + (1u << P.logC) - 1) >> P.logC) : P.batch;
@@ -28,6 +28,6 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   return STK_OK;
 }
 
-int stk_launch_pass_mont(stk_ctx* c, cudaStream_t s, const NttPass& P) {
-  return launch_pass_r<MontField, 2, 256, 2, false>(c, s, P, c->mont);
+int stk_launch_pass_stark_t11_cf(stk_ctx* c, cudaStream_t s, const NttPass& P) {
+  return launch_pass_r<StarkField, 3, 256, 2, 2>(c, s, P, StarkField());
 }
