@@ -413,9 +413,9 @@ def main():
       line["e2e"] = {"value": elems / e2e_s / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": cols * N * 32,
                      "d2h_bytes_per_step": cols * N * 32, "ms_per_step": e2e_s * 1e3,
                      "gb_per_s_each_way": cols * N * 32 / e2e_s / 1e9,
-                     "pcie_duplex_ceiling_gb_per_s_each_way": pcie_duplex,
-                     "note": "host-buffer API (stk_ntt_host): three-slot H2D / transform / D2H pipeline; bound by PCIe, "
-                             "ceiling = plain pinned copies both ways at once, measured in this run"}
+                     "pcie_duplex_plain_copies_gb_per_s_each_way": pcie_duplex,
+                     "note": "host-buffer API (stk_ntt_host): three-slot H2D / transform / D2H pipeline; bound by PCIe -- "
+                             "beside it, plain pinned 512 MiB copies both ways at once (two streams) in this run"}
     if not args.no_extras:
       try:
         line["extra"] = extras(eng, torch, stream, local)
