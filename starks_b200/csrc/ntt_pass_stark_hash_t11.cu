@@ -1,4 +1,4 @@
-// ntt_pass_stark_hash.cu -- final-pass instantiations with the fused Merkle bottom level (HASH in
+// ntt_pass_stark_hash_t11.cu -- (2048-element tiles; see ntt_pass_stark_hash.cu) final-pass instantiations with the fused Merkle bottom level (HASH in
 // ntt.cuh): the last pass of the LDE's forward transform also hashes the leaf pairs of every
 // tile as soon as all columns of the tile are stored, so the evaluations are hashed out of L2
 // while other CTAs still run butterflies (BLAKE2s is ALU work, the butterflies are bound by the
@@ -29,8 +29,6 @@ static int launch_hash_pass(stk_ctx* c, cudaStream_t s, const NttPass& P) {
   return STK_OK;
 }
 
-int stk_launch_pass_stark_hash_t11(stk_ctx* c, cudaStream_t s, const NttPass& P);  // ntt_pass_stark_hash_t11.cu
-
-int stk_launch_pass_stark_hash(stk_ctx* c, cudaStream_t s, const NttPass& P) {
-  return P.logT > 10 ? stk_launch_pass_stark_hash_t11(c, s, P) : launch_hash_pass<128, 4>(c, s, P);
+int stk_launch_pass_stark_hash_t11(stk_ctx* c, cudaStream_t s, const NttPass& P) {
+  return launch_hash_pass<256, 2>(c, s, P);
 }
