@@ -183,6 +183,26 @@ int stk_fri_prove(stk_ctx* ctx, const uint32_t* d_vals0, uint64_t n0, const uint
 int stk_constraint_eval(stk_ctx* ctx, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
                         uint64_t col_stride, const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs,
                         const uint8_t* h_mono_exps, uint64_t nmono, uint32_t* d_cev, uint64_t out_stride);
+/* construct_remainder_polynomials (stark.py:57-78) in EVALUATION form on the size-n domain <g2>:
+ * d_dev[j][i] = D_j(g2^i).  Where Z(x_i) != 0 (i != 0 mod ext) it is pointwise,
+ * D = C * (x - last) / (x^steps - 1) with x_i^steps one of ext constants; at i = 0 mod ext
+ * (both C and Z vanish) it is read from d_dsub = D_j on a subgroup of order sub_n containing
+ * <g2^ext> (the forward transform of D's coefficients, stk_quotient_z).  Saves 7/8 of D's
+ * size-n transform.  ext in 2..16; monomial list as stk_constraint_eval. */
+int stk_quotient_eval(stk_ctx* ctx, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                      uint64_t col_stride, const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs,
+                      const uint8_t* h_mono_exps, uint64_t nmono, const uint32_t g2[8], const uint32_t last[8],
+                      const uint32_t* d_dsub, uint64_t sub_n, uint64_t dsub_stride, uint32_t* d_dev,
+                      uint64_t out_stride);
+/* construct_boundary_polynomials (stark.py:80-104) in EVALUATION form on the size-n domain <g2>
+ * (STARK prime): d_bev[j][i] = (P_j(x_i) - (i0_j + i1_j*x_i)) / ((x_i - 1)(x_i - last)),
+ * last = g2^last_index (a non-zero multiple of ext), pointwise wherever the denominator is
+ * non-zero -- 1/(x_i - g2^e) = g2^-e * T[(i - e) mod n] with one cached table
+ * T[i] = (g2^i - 1)^-1 -- and from d_bsub (B_j on <g2^ext>, n/ext values per column) at
+ * i = 0 mod ext.  h_interp: width x {i0, i1} (8 limbs each).  Saves 7/8 of B's size-n transform. */
+int stk_boundary_eval(stk_ctx* ctx, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                      uint64_t col_stride, const uint32_t g2[8], uint64_t last_index, const uint32_t* h_interp,
+                      const uint32_t* d_bsub, uint64_t bsub_stride, uint32_t* d_bev, uint64_t out_stride);
 /* construct_remainder_polynomials (stark.py:57-78) on coefficient vectors of length n:
  * D = C / Z with Z = (X^steps - 1)/(X - last), computed as C*(X-last) / (X^steps - 1).
  * *h_bad = number of non-zero remainder coefficients (the reference asserts divisibility). */

@@ -60,6 +60,8 @@ SIGNATURES = {
     "stk_fri_fold4": (cint, [vp, vp, u64, u32p, u32p, vp]),
     "stk_fri_prove": (cint, [vp, vp, u64, vp, vp, u32p, u64, u64, u64, vp, u64, vp]),
     "stk_constraint_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, vp, u64]),
+    "stk_quotient_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, u32p, u32p, vp, u64, u64, vp, u64]),
+    "stk_boundary_eval": (cint, [vp, vp, u64, u64, u64, u64, u32p, u64, vp, vp, u64, vp, u64]),
     "stk_quotient_z": (cint, [vp, vp, u64, u64, u32p, vp, ctypes.POINTER(ctypes.c_uint32)]),
     "stk_div_linear": (cint, [vp, vp, u64, u32p, u64, vp]),
     "stk_lincomb": (cint, [vp, vp, u64, u64, u64, vp, vp]),

@@ -19,6 +19,8 @@ fe stk_h_pow(stk_ctx* c, const fe& a, uint64_t e) { return host::pow_u64(a, e, c
 fe stk_h_inv(stk_ctx* c, const fe& a) { return host::invmod(a, c->p); }
 fe stk_h_to_tw(stk_ctx* c, const fe& a) { return c->is_stark ? a : host::mulmod(a, c->mont.rone, c->p); }
 
+void stk_stark_release(stk_ctx* c);  // stark.cu: per-context inverse tables
+
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s && *s ? atoi(s) : dflt;
@@ -68,6 +70,7 @@ extern "C" __attribute__((visibility("default"))) void stk_destroy(stk_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& t : c->tables) cudaFree(t.d);
+  stk_stark_release(c);
   for (int i = 0; i < 10; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
   for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 3; ++i) if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);

@@ -52,6 +52,113 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const fe* __restri
   }
 }
 
+// D = C / Z on the evaluation domain itself (x_i = G2^i), pointwise wherever Z(x_i) != 0:
+// Z(x) = (x^steps - 1)/(x - last) and x_i^steps = omega^(i mod ext) (omega = G2^steps has order
+// ext), so D(x_i) = C(x_i) * (x_i - last) * inv[i mod ext] with the ext-1 constants
+// inv[r] = (omega^r - 1)^-1.  At i = 0 mod ext both C and Z vanish; those values (D on the
+// subgroup <G1>) come from D's coefficients through a small transform (dsub).  Replaces the
+// size-N transform of D for 7/8 of the points.
+struct QuotInv { fe v[16]; };  // inv[r] plain, r < ext <= 16
+template <class F>
+__global__ void __launch_bounds__(128) quotient_eval_kernel(const fe* __restrict__ pev, uint64_t n, uint64_t ext,
+                                                            uint32_t width, uint64_t col_stride,
+                                                            const Monomial* __restrict__ monos, uint32_t nmono,
+                                                            const fe* __restrict__ X, int xshift, fe last_tw,
+                                                            const QuotInv inv, const fe* __restrict__ dsub,
+                                                            uint64_t dsub_stride, uint64_t sub_step,
+                                                            fe* __restrict__ dev, uint64_t out_stride, const F f) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t r = i % ext;
+  if (r == 0) {
+    const uint64_t k = (i / ext) * sub_step;
+    for (uint32_t j = 0; j < width; ++j) fe_store(dev + j * out_stride + i, fe_load(dsub + j * dsub_stride + k));
+    return;
+  }
+  fe st_tw[12];
+  for (uint32_t k = 0; k < width; ++k) st_tw[k] = f.to_tw(fe_load(pev + k * col_stride + i));
+  const uint64_t inext = (i + ext) % n;
+  // (x_i - last) * inv[r], back in twiddle form for the final product
+  const fe xm = f.sub(fe_load_ro(X + (i << xshift)), last_tw);
+  const fe fac_tw = f.to_tw(f.mul_tw(inv.v[r], xm));
+  for (uint32_t j = 0; j < width; ++j) {
+    fe acc = fe_zero();
+    for (uint32_t m = 0; m < nmono; ++m) {
+      if (monos[m].out != j) continue;
+      fe term = f.from_tw(monos[m].coeff_tw);
+      for (uint32_t k = 0; k < width; ++k)
+        for (uint32_t e = 0; e < monos[m].exp[k]; ++e) term = f.mul_tw(term, st_tw[k]);
+      acc = f.add(acc, term);
+    }
+    const fe cval = f.sub(fe_load(pev + j * col_stride + inext), acc);
+    fe_store(dev + j * out_stride + i, f.mul_tw(cval, fac_tw));
+  }
+}
+
+// ---- B = (P - I) / ((X - 1)(X - last)) on the evaluation domain, pointwise (STARK prime) ----
+// 1/(x_i - a) for a = G2^e in the domain is a^-1 * T[(i - e) mod n] with ONE cached table
+// T[i] = (G2^i - 1)^-1, i >= 1 (built once per (G2, n) by chunked batch inversion).
+constexpr int kInvChunk = 32;
+__device__ __forceinline__ fe stark_inv(const StarkField& f, const fe& a) {  // a^(p-2)
+  fe e = StarkField::modulus();  // limbs {1, 0xFFFFFEA1, ...}: p - 2 borrows out of limb 0
+  e.v[0] = 0xFFFFFFFFu;
+  e.v[1] -= 1u;
+  fe r = fe_zero();
+  r.v[0] = 1;
+  fe base = a;
+  for (int i = 0; i < 256; ++i) {
+    if ((e.v[i >> 5] >> (i & 31)) & 1u) r = f.mul_tw(r, base);
+    base = f.mul_tw(base, base);
+  }
+  return r;
+}
+// T[i] = (X[i] - 1)^-1 for i in [1, n); T[0] = 0.  One thread per chunk of kInvChunk entries:
+// prefix products parked in T itself, one inversion, then the backward sweep (Montgomery's trick).
+__global__ void __launch_bounds__(128) invtable_kernel(const fe* __restrict__ X, int xshift, uint64_t n, fe* __restrict__ T) {
+  const StarkField f;
+  const uint64_t c0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * kInvChunk;
+  if (c0 >= n) return;
+  const uint64_t c1 = c0 + kInvChunk < n ? c0 + kInvChunk : n;
+  fe one = fe_zero();
+  one.v[0] = 1;
+  fe acc = one;
+  for (uint64_t i = c0; i < c1; ++i) {
+    const fe v = i ? f.sub(fe_load_ro(X + (i << xshift)), one) : one;
+    acc = f.mul_tw(acc, v);
+    fe_store(T + i, acc);
+  }
+  fe inv = stark_inv(f, acc);
+  for (uint64_t i = c1; i-- > c0;) {
+    const fe v = i ? f.sub(fe_load_ro(X + (i << xshift)), one) : one;
+    const fe prev = i > c0 ? fe_load(T + i - 1) : one;
+    fe_store(T + i, i ? f.mul_tw(inv, prev) : fe_zero());
+    inv = f.mul_tw(inv, v);
+  }
+}
+struct BoundaryInterp { fe i0[12], i1[12]; };
+__global__ void __launch_bounds__(128) boundary_eval_kernel(const fe* __restrict__ pev, uint64_t n, uint64_t ext, uint32_t width,
+                                                            uint64_t col_stride, const fe* __restrict__ X, int xshift,
+                                                            const fe* __restrict__ T, uint64_t last_index, fe last_inv,
+                                                            const BoundaryInterp I, const fe* __restrict__ bsub,
+                                                            uint64_t bsub_stride, fe* __restrict__ bev, uint64_t out_stride) {
+  const StarkField f;
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i % ext == 0) {
+    for (uint32_t j = 0; j < width; ++j) fe_store(bev + j * out_stride + i, fe_load(bsub + j * bsub_stride + i / ext));
+    return;
+  }
+  const fe x = fe_load_ro(X + (i << xshift));
+  const uint64_t il = i >= last_index ? i - last_index : i + n - last_index;  // != 0: last_index is a multiple of ext
+  // 1/((x - 1)(x - last)) = T[i] * last^-1 * T[i - last_index]
+  const fe inv = f.mul_tw(f.mul_tw(fe_load(T + i), fe_load(T + il)), last_inv);
+  for (uint32_t j = 0; j < width; ++j) {
+    const fe ix = f.add(I.i0[j], f.mul_tw(I.i1[j], x));
+    const fe num = f.sub(fe_load(pev + j * col_stride + i), ix);
+    fe_store(bev + j * out_stride + i, f.mul_tw(num, inv));
+  }
+}
+
 // E = C*(X - last) has coefficients e[i] = c[i-1] - last*c[i] (c[-1] = c[n] = 0, i <= n).
 template <class F>
 __device__ __forceinline__ fe e_coeff(const fe* c, uint64_t n, uint64_t i, const fe& last_tw, const F& f) {
@@ -237,6 +344,124 @@ STK_API int stk_constraint_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, u
     constraint_eval_kernel<MontField><<<blocks, 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
                                                                      (const Monomial*)t, (uint32_t)nmono, (fe*)d_cev,
                                                                      out_stride, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+// construct_remainder_polynomials (stark.py:57-78) in evaluation form on the size-n domain <g2>:
+// d_dev[j][i] = D_j(g2^i) from the trace evaluations d_pev (n per column) wherever Z does not
+// vanish, and from d_dsub (D_j on a subgroup of order sub_n containing <g2^ext>, e.g. the forward
+// transform of D's coefficients) at i = 0 mod ext.  ext <= 16.
+STK_API int stk_quotient_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                              uint64_t col_stride, const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs,
+                              const uint8_t* h_mono_exps, uint64_t nmono, const uint32_t g2[8], const uint32_t last[8],
+                              const uint32_t* d_dsub, uint64_t sub_n, uint64_t dsub_stride, uint32_t* d_dev,
+                              uint64_t out_stride) {
+  if (!c || !d_pev || !d_dev || !d_dsub || !g2 || !last || (nmono && (!h_mono_out || !h_mono_coeffs || !h_mono_exps)))
+    return STK_EINVAL;
+  if (width == 0 || width > 12) return stk_fail(c, STK_EUNSUPPORTED, "state width must be in 1..12");
+  if (ext < 2 || ext > 16 || n % ext) return stk_fail(c, STK_EUNSUPPORTED, "extension factor must be in 2..16 and divide n");
+  const uint64_t steps = n / ext;
+  if (sub_n == 0 || sub_n % steps) return stk_fail(c, STK_EINVAL, "d_dsub must cover a subgroup containing <g2^ext>");
+  std::vector<Monomial> ms(nmono ? nmono : 1);
+  for (uint64_t m = 0; m < nmono; ++m) {
+    if (h_mono_out[m] >= width) return stk_fail(c, STK_EINVAL, "monomial output index out of range");
+    fe cf = host::reduce(stk_load_fe(h_mono_coeffs + 8 * m), c->p);
+    ms[m].coeff_tw = stk_h_to_tw(c, cf);
+    ms[m].out = h_mono_out[m];
+    for (uint64_t k = 0; k < 12; ++k) ms[m].exp[k] = k < width ? h_mono_exps[width * m + k] : 0;
+  }
+  const fe G2 = host::reduce(stk_load_fe(g2), c->p);
+  const fe one = host::reduce(host::from_u64(1), c->p);
+  if (!fe_eq(stk_h_pow(c, G2, n), one)) return stk_fail(c, STK_EINVAL, "g2^n != 1");
+  const fe omega = stk_h_pow(c, G2, steps);
+  QuotInv inv;
+  for (int r = 0; r < 16; ++r) inv.v[r] = fe_zero();
+  fe wr = omega;
+  for (uint64_t r = 1; r < ext; ++r) {
+    fe den = host::submod(wr, one, c->p);
+    if (fe_is_zero(den)) return stk_fail(c, STK_EINVAL, "g2^steps has order below ext");
+    inv.v[r] = stk_h_inv(c, den);
+    wr = stk_h_mul(c, wr, omega);
+  }
+  const fe* X;
+  uint64_t xs = 1;
+  STK_TRY(stk_get_table_strided(c, G2, n, &X, &xs));
+  int xshift = 0;
+  while ((1ull << xshift) < xs) ++xshift;
+  if ((1ull << xshift) != xs) { STK_TRY(stk_get_table(c, G2, n, &X)); xshift = 0; }
+  void* t;
+  STK_TRY(stk_scratch(c, 2, ms.size() * sizeof(Monomial), &t));
+  STK_CUDA(c, cudaMemcpyAsync(t, ms.data(), ms.size() * sizeof(Monomial), cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));  // ms is a stack-owned staging buffer
+  const fe last_tw = stk_h_to_tw(c, host::reduce(stk_load_fe(last), c->p));
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (c->is_stark)
+    quotient_eval_kernel<StarkField><<<blocks, 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
+                                                                    (const Monomial*)t, (uint32_t)nmono, X, xshift, last_tw, inv,
+                                                                    (const fe*)d_dsub, dsub_stride, sub_n / steps, (fe*)d_dev,
+                                                                    out_stride, StarkField());
+  else
+    quotient_eval_kernel<MontField><<<blocks, 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
+                                                                   (const Monomial*)t, (uint32_t)nmono, X, xshift, last_tw, inv,
+                                                                   (const fe*)d_dsub, dsub_stride, sub_n / steps, (fe*)d_dev,
+                                                                   out_stride, c->mont);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+// construct_boundary_polynomials (stark.py:80-104) in evaluation form on the size-n domain <g2>
+// (STARK prime only): d_bev[j][i] = (P_j(x_i) - (i0_j + i1_j x_i)) / ((x_i - 1)(x_i - last)) with
+// last = g2^last_index (a multiple of ext), pointwise wherever the denominator is non-zero; the
+// values at i = 0 mod ext come from d_bsub = B_j on <g2^ext> (transform of B's coefficients).
+namespace {
+struct InvTable { stk_ctx* c; fe root; uint64_t n; fe* d; };
+std::vector<InvTable> g_invtables;
+}  // namespace
+void stk_stark_release(stk_ctx* c) {
+  for (size_t i = 0; i < g_invtables.size();) {
+    if (g_invtables[i].c == c) { cudaFree(g_invtables[i].d); g_invtables.erase(g_invtables.begin() + i); }
+    else ++i;
+  }
+}
+STK_API int stk_boundary_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
+                              uint64_t col_stride, const uint32_t g2[8], uint64_t last_index, const uint32_t* h_interp,
+                              const uint32_t* d_bsub, uint64_t bsub_stride, uint32_t* d_bev, uint64_t out_stride) {
+  if (!c || !d_pev || !d_bev || !d_bsub || !g2 || !h_interp) return STK_EINVAL;
+  if (!c->is_stark) return stk_fail(c, STK_EUNSUPPORTED, "pointwise boundary quotient is built for the STARK prime");
+  if (width == 0 || width > 12) return stk_fail(c, STK_EUNSUPPORTED, "state width must be in 1..12");
+  if (ext < 2 || n % ext || last_index % ext || last_index >= n || last_index == 0)
+    return stk_fail(c, STK_EINVAL, "last_index must be a non-zero multiple of ext below n");
+  const fe G2 = host::reduce(stk_load_fe(g2), c->p);
+  const fe one = host::reduce(host::from_u64(1), c->p);
+  if (!fe_eq(stk_h_pow(c, G2, n), one) || fe_eq(stk_h_pow(c, G2, n / 2), one))
+    return stk_fail(c, STK_EINVAL, "g2 is not a primitive n-th root of unity");
+  const fe* X;
+  uint64_t xs = 1;
+  STK_TRY(stk_get_table_strided(c, G2, n, &X, &xs));
+  int xshift = 0;
+  while ((1ull << xshift) < xs) ++xshift;
+  if ((1ull << xshift) != xs) { STK_TRY(stk_get_table(c, G2, n, &X)); xshift = 0; }
+  fe* T = nullptr;
+  for (auto& t : g_invtables)
+    if (t.c == c && t.n == n && fe_eq(t.root, G2)) T = t.d;
+  if (!T) {
+    if (g_invtables.size() >= 8) { STK_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(g_invtables.front().d); g_invtables.erase(g_invtables.begin()); }
+    STK_CUDA(c, cudaMalloc(&T, n * sizeof(fe)));
+    const uint64_t chunks = (n + kInvChunk - 1) / kInvChunk;
+    invtable_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, c->stream>>>(X, xshift, n, T);
+    STK_CUDA(c, cudaGetLastError());
+    g_invtables.push_back({c, G2, n, T});
+  }
+  BoundaryInterp I;
+  for (uint64_t j = 0; j < 12; ++j) {
+    I.i0[j] = j < width ? host::reduce(stk_load_fe(h_interp + 16 * j), c->p) : fe_zero();
+    I.i1[j] = j < width ? host::reduce(stk_load_fe(h_interp + 16 * j + 8), c->p) : fe_zero();
+  }
+  const fe last_inv = stk_h_inv(c, stk_h_pow(c, G2, last_index));
+  boundary_eval_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const fe*)d_pev, n, ext, (uint32_t)width, col_stride,
+                                                                          X, xshift, T, last_index, last_inv, I,
+                                                                          (const fe*)d_bsub, bsub_stride, (fe*)d_bev, out_stride);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }

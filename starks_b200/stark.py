@@ -10,12 +10,13 @@ Fiat-Shamir scalars and the opened branches cross to the host.  The proof object
 [m_root, l_root, branches, fri_proof] (stark.py:270-277) is bit-identical to the reference's.
 verify_proof is host-side glue (80 positions + FRI checks) mirroring stark.py:281-372."""
 import ctypes
+import os
 import time
 from hashlib import blake2s
 
 import numpy as np
 
-from .engine import default_engine
+from .engine import P_STARK, default_engine
 from .fri import FRI, DeviceLayer
 from .limbs import int_to_limbs, ints_to_limbs, limbs_to_ints
 from .merkle_tree import unpack_merkle_leaf, verify_branch
@@ -130,7 +131,10 @@ class STARK(object):
       eng._check(eng.lib.stk_memset(eng.ctx, d_coef.ptr, 0, 3 * w * cs * E))
     # construct_trace_polynomials (:27-36): inverse transform over <G1>
     eng.ntt(d_trace.ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
-    if not merged:
+    # D's evaluations can be taken pointwise from P's wherever Z does not vanish (stk_quotient_eval):
+    # then only P and B go through the size-N transform
+    pointwise_d = merged and 2 <= ext <= 16 and os.environ.get("STK_PROOF_POINTWISE", "1") != "0"
+    if not merged or pointwise_d:
       eng.ntt(d_coef.ptr, steps, cs, d_cols.ptr, N, N, w, G2)            # evaluation of P (:254-256)
     if M == N:
       pev_ptr, pev_stride = d_cols.ptr, N
@@ -151,7 +155,13 @@ class STARK(object):
       eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
                                         dst, ctypes.byref(bad)))
       assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
-    if not merged:
+    if pointwise_d:
+      # D on <G_M> (contains <G1>, where Z vanishes) from its coefficients, everything else pointwise
+      eng.ntt(d_coef.at(w * cs * E), M, cs, d_t1.ptr, M, M, w, GM)
+      eng._check(eng.lib.stk_quotient_eval(eng.ctx, d_cols.ptr, N, ext, w, N, h_out.ctypes.data, h_coef.ctypes.data,
+                                           h_exp.ctypes.data, nm, int_to_limbs(G2).ctypes.data_as(u32p),
+                                           last_l.ctypes.data_as(u32p), d_t1.ptr, M, M, d_cols.at(w * N * E), N))
+    elif not merged:
       eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
     # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
     out_vals = limbs_to_ints(tr[:, -1, :])
@@ -170,7 +180,17 @@ class STARK(object):
       eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
       if merged:   # the quotient has steps-2 coefficients; clear the two stale ones above it
         eng._check(eng.lib.stk_memset(eng.ctx, a + (steps - 2) * E, 0, 2 * E))
-    if merged:
+    if pointwise_d and p == P_STARK and steps >= 2:
+      # B on <G1> (holds x = 1 and x = last, where the denominator vanishes) from its coefficients,
+      # everything else pointwise from P's evaluations (stk_boundary_eval)
+      eng.ntt(d_coef.at(2 * w * cs * E), steps, cs, d_t2.ptr, steps, steps, w, pow(G2, ext, p))
+      h_interp = ints_to_limbs(interps)
+      eng._check(eng.lib.stk_boundary_eval(eng.ctx, d_cols.ptr, N, ext, w, N, int_to_limbs(G2).ctypes.data_as(u32p),
+                                           (steps - 1) * ext, h_interp.ctypes.data, d_t2.ptr, steps,
+                                           d_cols.at(2 * w * N * E), N))
+    elif pointwise_d:
+      eng.ntt(d_coef.at(2 * w * cs * E), cs, cs, d_cols.at(2 * w * N * E), N, N, w, G2)   # evaluation of B
+    elif merged:
       eng.ntt(d_coef.ptr, cs, cs, d_cols.ptr, N, N, 3 * w, G2)           # evaluation of P, D, B (:254-256)
     else:
       eng.ntt(d_t2.ptr, steps - 2, steps, d_cols.at(2 * w * N * E), N, N, w, G2)

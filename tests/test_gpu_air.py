@@ -70,3 +70,35 @@ def test_small_prime_field(eng, oracle):
   got = witness_limbs(F, [4], 40, 1, sp, engine=eng)
   assert oracle.from_limbs(got[0]) == want[0]
   eng.set_field(P)
+
+
+def test_pointwise_quotients_equal_transform_route(eng, oracle, monkeypatch):
+  """For degree-1 AIRs mk_proof takes D and B pointwise from P's evaluations (stk_quotient_eval,
+  stk_boundary_eval) instead of transforming their coefficients; both routes must give the same
+  columns and the same proof, and the oracle's proof where it is cheap enough."""
+  from starks_b200.air import witness_limbs
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  F = IntegersModP(P)
+  cases = [(64, 8, [3, 5], [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]),
+           (256, 16, [1, 2, 3], [{(0, 1, 0): 1}, {(0, 0, 1): 1, (0, 0, 0): 5}, {(1, 0, 0): 7, (0, 1, 0): P - 2, (0, 0, 0): 11}]),
+           (1 << 12, 8, [9], [{(1,): 3, (0,): 1}])]
+  for steps, ext, inp, sp in cases:
+    width = len(inp)
+    w = witness_limbs(F, inp, steps, width, sp, engine=eng)
+    boundary = [(0, j, inp[j]) for j in range(width)]
+    S = STARK(F, steps, ext, width, sp, engine=eng)
+    got = {}
+    for mode in ("1", "0"):
+      monkeypatch.setenv("STK_PROOF_POINTWISE", mode)
+      proof = S.mk_proof(w, boundary, keep_device=True)
+      cols = S.device["cols"].download((3 * width, steps * ext, 8))
+      for b in S.device.values():
+        b.free()
+      got[mode] = (proof, cols)
+    assert (got["1"][1] == got["0"][1]).all(), (steps, ext)
+    assert got["1"][0] == got["0"][0]
+    assert S.verify_proof(got["1"][0], w, boundary)
+    if steps <= 256:
+      want = oracle.StarkOracle(steps, ext, width, sp).mk_proof(oracle.computational_trace(P, inp, steps, sp), boundary)
+      assert got["1"][0] == want
