@@ -393,7 +393,13 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     const int logns = logn - 3;
     const uint64_t ns = n >> 3, vb = batch * 8;
     STK_TRY(build_plan(logns, vb, plan, ntt_max_radix()));
-    if (vb <= 0x7fffffffull && (plan.size() == 1 || vb <= 65535)) {
+    std::vector<NttPass> whole;
+    STK_TRY(build_plan(logn, batch, whole, ntt_max_radix()));
+    // only where it saves a pass over HBM (N >= 2^23): at equal pass counts the two routes time the
+    // same on one GPU (2^21: 17.87 ms both) and the coset route measured slower inside the NCCL
+    // sharded commit (profiles/r01b_dist_2gpu.txt), so the long transform keeps the expansion round
+    const bool fewer_passes = plan.size() < whole.size() || env_int("STK_LDE_COSET", 1) > 1;
+    if (fewer_passes && vb <= 0x7fffffffull && (plan.size() == 1 || vb <= 65535)) {
       fe* tmpc = nullptr;
       if (plan.size() > 1) {
         void* t;

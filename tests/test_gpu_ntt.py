@@ -148,3 +148,28 @@ def test_large_sizes_by_properties(eng, oracle, logn, batch):
     x = pow(w, k, P)
     want = sum(cf * pow(x, i, P) for i, cf in zip(idx, coef)) % P
     assert oracle.from_limbs(evs[k:k + 1])[0] == want, k
+
+
+def test_zero_padded_routes_agree(eng, oracle, monkeypatch):
+  """A zero-padded forward transform (n_in <= N/8) has two routes: the expansion round of the long
+  transform and eight coset transforms over <w^8> (ntt.cuh, cshift).  Both must give the same
+  evaluations, and the oracle's where it is cheap."""
+  import numpy as np
+  rng = np.random.default_rng(9)
+  for logn, cols, n_in in ((6, 3, 8), (9, 5, 33), (12, 4, 512), (15, 2, 4096), (16, 70, 8192), (21, 2, 1 << 18)):
+    n = 1 << logn
+    w = pow(7, (P - 1) // n, P)
+    a = rng.integers(0, 2**32, size=(cols, n_in, 8), dtype=np.uint64).astype(np.uint32)
+    a[:, :, 7] &= 0x7FFFFFFF
+    d_in = eng.alloc(a.nbytes).upload(a)
+    d_out = eng.alloc(cols * n * 32)
+    got = {}
+    for mode in ("0", "2"):
+      monkeypatch.setenv("STK_LDE_COSET", mode)
+      eng._check(eng.lib.stk_memset(eng.ctx, d_out.ptr, 0x5A, cols * n * 32))
+      eng.ntt(d_in.ptr, n_in, n_in, d_out.ptr, n, n, cols, w)
+      got[mode] = d_out.download((cols, n, 8))
+    assert (got["0"] == got["2"]).all(), (logn, cols, n_in)
+    if logn <= 12:
+      assert (got["2"] == oracle.fft_limbs(P, w, a, n)).all()
+    d_in.free(); d_out.free()
