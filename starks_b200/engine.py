@@ -52,11 +52,14 @@ class DevBuf:
   def at(self, byte_offset):
     return self.ptr + int(byte_offset)
 
-  def upload(self, arr, byte_offset=0):
+  def upload(self, arr, byte_offset=0, wait=True):
+    """wait=False: the caller keeps `arr` alive and unchanged until the stream is next synchronised
+    (pinned sources then copy while the host goes on enqueueing)."""
     arr = np.ascontiguousarray(arr)
     assert byte_offset + arr.nbytes <= self.nbytes
     self.eng._check(self.eng.lib.stk_memcpy_h2d(self.eng.ctx, self.ptr + byte_offset, arr.ctypes.data, arr.nbytes))
-    self.eng.sync()  # pageable source: keep it alive until the copy is done
+    if wait:
+      self.eng.sync()  # pageable source: keep it alive until the copy is done
     return self
 
   def download(self, shape, dtype=np.uint32, byte_offset=0):

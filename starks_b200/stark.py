@@ -97,7 +97,7 @@ class STARK(object):
     tr = self._witness_limbs(witness)
     assert tr.shape[1] == steps
     E = 32
-    d_trace = eng.alloc(w * steps * E).upload(tr)
+    d_trace = eng.alloc(w * steps * E).upload(tr, wait=False)   # `tr` lives until the syncs below
     d_cols = eng.alloc(3 * w * N * E)        # rows: P_1..P_w, D_1..D_w, B_1..B_w (stark.py:247)
     d_t1 = eng.alloc(w * N * E)
     d_t2 = eng.alloc(w * N * E)
