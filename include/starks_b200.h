@@ -161,6 +161,10 @@ int stk_verify_branches(stk_ctx* ctx, const uint8_t root[32], uint64_t n, uint64
  * reference does not reduce it, fri.py:229). */
 int stk_fri_fold4(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, const uint32_t root[8],
                   const uint32_t special_x[8], uint32_t* d_out);
+/* get_pseudorandom_indices (starks/utils.py:60-90) as the FRI driver derives them (host BLAKE2s
+ * chain over the 32-byte entropy, 4-byte big-endian words).  Host only: ctx may be NULL. */
+int stk_pseudorandom_indices(stk_ctx* ctx, const uint8_t entropy[32], uint64_t modulus, uint64_t count,
+                             uint64_t exclude_multiples_of, uint64_t* h_out);
 /* The whole commit phase of SmoothSubgroupFRI.generate_proximity_proof (starks/fri.py:189-266)
  * for evaluations already on the device: per layer fold, column tree, Fiat-Shamir indices
  * (starks/utils.py:60-90) and branch gathers, one host synchronisation per layer.  d_nodes0 /

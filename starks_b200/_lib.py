@@ -58,6 +58,7 @@ SIGNATURES = {
     "stk_merkle_paths": (cint, [vp, vp, u64, u64, u64, vp, vp, u64, vp, u64]),
     "stk_verify_branches": (cint, [vp, vp, u64, u64, vp, u64, vp, u64, vp]),
     "stk_fri_fold4": (cint, [vp, vp, u64, u32p, u32p, vp]),
+    "stk_pseudorandom_indices": (cint, [vp, vp, u64, u64, u64, vp]),
     "stk_fri_prove": (cint, [vp, vp, u64, vp, vp, u32p, u64, u64, u64, vp, u64, vp]),
     "stk_constraint_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, vp, u64]),
     "stk_quotient_eval": (cint, [vp, vp, u64, u64, u64, u64, vp, vp, vp, u64, u32p, u32p, vp, u64, u64, vp, u64]),

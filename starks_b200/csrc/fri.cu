@@ -121,6 +121,20 @@ uint64_t rec_bytes_for(uint64_t n) {
 
 }  // namespace
 
+// get_pseudorandom_indices (starks/utils.py:60-90) exactly as the FRI driver derives them; needs no
+// device (ctx may be NULL), so the host BLAKE2s and the index rule are testable on a CPU-only box.
+extern "C" __attribute__((visibility("default"))) int stk_pseudorandom_indices(stk_ctx* c, const uint8_t entropy[32],
+                                                                                uint64_t modulus, uint64_t count,
+                                                                                uint64_t exclude_multiples_of,
+                                                                                uint64_t* h_out) {
+  if (!entropy || !h_out) return STK_EINVAL;
+  if (exclude_multiples_of == 1) return stk_fail(c, STK_EINVAL, "exclude_multiples_of = 1 leaves no positions");
+  std::vector<uint64_t> v;
+  STK_TRY(fri_indices(c, entropy, modulus, count, exclude_multiples_of, v));
+  for (uint64_t i = 0; i < count; ++i) h_out[i] = v[i];
+  return STK_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int stk_fri_prove(
     stk_ctx* c, const uint32_t* d_vals0, uint64_t n0, const uint8_t* d_nodes0, const uint8_t* h_root0,
     const uint32_t root[8], uint64_t maxdeg_plus_1, uint64_t exclude, uint64_t security, uint8_t* h_out,
