@@ -133,7 +133,7 @@ class STARK(object):
     eng.ntt(d_trace.ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
     # D's evaluations can be taken pointwise from P's wherever Z does not vanish (stk_quotient_eval):
     # then only P and B go through the size-N transform
-    pointwise_d = merged and 2 <= ext <= 16 and os.environ.get("STK_PROOF_POINTWISE", "1") != "0"
+    pointwise_d = M < N and 2 <= ext <= 16 and os.environ.get("STK_PROOF_POINTWISE", "1") != "0"
     if not merged or pointwise_d:
       eng.ntt(d_coef.ptr, steps, cs, d_cols.ptr, N, N, w, G2)            # evaluation of P (:254-256)
     if M == N:
@@ -157,10 +157,11 @@ class STARK(object):
       assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
     if pointwise_d:
       # D on <G_M> (contains <G1>, where Z vanishes) from its coefficients, everything else pointwise
-      eng.ntt(d_coef.at(w * cs * E), M, cs, d_t1.ptr, M, M, w, GM)
+      dco, dco_stride, dsub = (d_coef.at(w * cs * E), cs, d_t1) if merged else (d_t1.ptr, M, d_t2)
+      eng.ntt(dco, M, dco_stride, dsub.ptr, M, M, w, GM)
       eng._check(eng.lib.stk_quotient_eval(eng.ctx, d_cols.ptr, N, ext, w, N, h_out.ctypes.data, h_coef.ctypes.data,
                                            h_exp.ctypes.data, nm, int_to_limbs(G2).ctypes.data_as(u32p),
-                                           last_l.ctypes.data_as(u32p), d_t1.ptr, M, M, d_cols.at(w * N * E), N))
+                                           last_l.ctypes.data_as(u32p), dsub.ptr, M, M, d_cols.at(w * N * E), N))
     elif not merged:
       eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
     # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
@@ -180,15 +181,16 @@ class STARK(object):
       eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
       if merged:   # the quotient has steps-2 coefficients; clear the two stale ones above it
         eng._check(eng.lib.stk_memset(eng.ctx, a + (steps - 2) * E, 0, 2 * E))
-    if pointwise_d and p == P_STARK and steps >= 2:
+    if pointwise_d and p == P_STARK and steps >= 4:
       # B on <G1> (holds x = 1 and x = last, where the denominator vanishes) from its coefficients,
       # everything else pointwise from P's evaluations (stk_boundary_eval)
-      eng.ntt(d_coef.at(2 * w * cs * E), steps, cs, d_t2.ptr, steps, steps, w, pow(G2, ext, p))
+      bco, bco_stride, bsub = (d_coef.at(2 * w * cs * E), cs, d_t2) if merged else (d_t2.ptr, steps, d_t1)
+      eng.ntt(bco, steps - 2, bco_stride, bsub.ptr, steps, steps, w, pow(G2, ext, p))
       h_interp = ints_to_limbs(interps)
       eng._check(eng.lib.stk_boundary_eval(eng.ctx, d_cols.ptr, N, ext, w, N, int_to_limbs(G2).ctypes.data_as(u32p),
-                                           (steps - 1) * ext, h_interp.ctypes.data, d_t2.ptr, steps,
+                                           (steps - 1) * ext, h_interp.ctypes.data, bsub.ptr, steps,
                                            d_cols.at(2 * w * N * E), N))
-    elif pointwise_d:
+    elif pointwise_d and merged:
       eng.ntt(d_coef.at(2 * w * cs * E), cs, cs, d_cols.at(2 * w * N * E), N, N, w, G2)   # evaluation of B
     elif merged:
       eng.ntt(d_coef.ptr, cs, cs, d_cols.ptr, N, N, 3 * w, G2)           # evaluation of P, D, B (:254-256)

@@ -73,7 +73,7 @@ def test_small_prime_field(eng, oracle):
 
 
 def test_pointwise_quotients_equal_transform_route(eng, oracle, monkeypatch):
-  """For degree-1 AIRs mk_proof takes D and B pointwise from P's evaluations (stk_quotient_eval,
+  """Whenever the constraint subgroup is smaller than the domain mk_proof takes D and B pointwise from P's evaluations (stk_quotient_eval,
   stk_boundary_eval) instead of transforming their coefficients; both routes must give the same
   columns and the same proof, and the oracle's proof where it is cheap enough."""
   from starks_b200.air import witness_limbs
@@ -82,7 +82,9 @@ def test_pointwise_quotients_equal_transform_route(eng, oracle, monkeypatch):
   F = IntegersModP(P)
   cases = [(64, 8, [3, 5], [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]),
            (256, 16, [1, 2, 3], [{(0, 1, 0): 1}, {(0, 0, 1): 1, (0, 0, 0): 5}, {(1, 0, 0): 7, (0, 1, 0): P - 2, (0, 0, 0): 11}]),
-           (1 << 12, 8, [9], [{(1,): 3, (0,): 1}])]
+           (1 << 12, 8, [9], [{(1,): 3, (0,): 1}]),
+           (128, 8, [2, 3], [{(0, 1): 1}, {(1, 0): 1, (0, 2): 1}]),           # degree 2: M = 2 * steps
+           (64, 8, [3], [{(3,): 1, (1,): 2, (0,): 5}])]                        # degree 3: M = 4 * steps
   for steps, ext, inp, sp in cases:
     width = len(inp)
     w = witness_limbs(F, inp, steps, width, sp, engine=eng)
