@@ -230,12 +230,38 @@ int stk_trace_generate(stk_ctx* ctx, const uint32_t* h_inp, uint64_t steps, uint
                        const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs, const uint8_t* h_mono_exps,
                        uint64_t nmono, uint32_t* h_witness);
 
+/* The same trace generated ON THE DEVICE (trace.cu): d_witness[(t*width + dim)*stride + step]
+ * for `ntraces` independent traces with inputs h_inp[t][dim].  Parallel over traces (one thread
+ * each) and, for AIRs whose step polynomials have degree <= 1, over chunks of one trace: the
+ * chunk-start states come from powers of the (width+1)^2 companion matrix (a prefix over A^L on
+ * the host, ~(width+1)^2 multiplies per chunk), every chunk's links run in their own thread.
+ * Asynchronous on the context's stream. */
+int stk_trace_generate_dev(stk_ctx* ctx, const uint32_t* h_inp, uint64_t ntraces, uint64_t steps, uint64_t width,
+                           const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs, const uint8_t* h_mono_exps,
+                           uint64_t nmono, uint32_t* d_witness, uint64_t stride);
+/* stk_trace_generate into h_witness (pinned) with every finished block of 2^15 steps copied to
+ * d_witness[dim*stride + step] while the next block is computed (upload hidden behind the
+ * recurrence).  Returns with the copies enqueued. */
+int stk_trace_generate_upload(stk_ctx* ctx, const uint32_t* h_inp, uint64_t steps, uint64_t width,
+                              const uint32_t* h_mono_out, const uint32_t* h_mono_coeffs, const uint8_t* h_mono_exps,
+                              uint64_t nmono, uint32_t* h_witness, uint32_t* d_witness, uint64_t stride);
+/* *h_bad = number of elements of d_vals[0..n) that are not canonical residues (>= p): the kernels
+ * assume canonical operands (IntegerModP.__init__ reduces, starks/modp.py:35-36).  sync != 0:
+ * returns with *h_bad written; sync == 0: h_bad must be pinned host memory (stk_host_alloc) and
+ * holds the count once the context's stream has been synchronised. */
+int stk_count_noncanonical(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, uint32_t* h_bad, int sync);
+
 /* ---- K0: integer-pipe microbenchmarks (roofline denominators) ---------------------- */
 /* which: 0 IMAD, 1 IMAD.WIDE, 2 IADD3, 3 IMAD.HI, 4 IADD3+LOP3+SHF (BLAKE2s mix),
  * 5 field multiply, 6 NTT butterfly, 7 IMAD+IADD3, 8 IMAD.WIDE+IADD3, 9 carry-chain adds,
  * 10 IMAD.WIDE.X carry rows.  Returns elapsed milliseconds and the number of
  * operations (of the kind named) executed. */
 int stk_microbench(stk_ctx* ctx, int which, uint64_t iters, float* ms, double* ops);
+/* A/B of the experimental multiply (csrc/field_exp.cuh) in registers: which = 5 | 6 as above,
+ * variant 0 = production, bit 0 = accumulators without zero-initialisation, bit 1 = aligned
+ * 351*H rows.  *mismatches counts outputs that differ from the production kernel's (must be 0). */
+int stk_microbench_variant(stk_ctx* ctx, int variant, int which, uint64_t iters, float* ms, double* ops,
+                           uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -1,14 +1,15 @@
 """Loader for the upstream pure-Python reference (TEST INFRASTRUCTURE ONLY).
 
-Imports `starks` from /root/reference (present only in the authoring container, never
-on the GPU box) and applies the two-line restoration SURVEY.md App. B documents:
+Imports `starks` from the unmodified copy staged under baseline/_ref/ (git-ignored; made by
+baseline/stage_ref.py, shipped to the GPU box by gpurun) or from /root/reference (authoring
+container only) and applies the two-line restoration SURVEY.md App. B documents:
 the multiplicative-subgroup FRI in starks/fri.py:176-366 is commented out at HEAD, so
 the leading '#' of those lines is dropped at load time and `FRI = SmoothSubgroupFRI`
 is appended.  No reference source is copied into this repository; the module source
 is read, patched in memory and exec'd.
 
-Only oracle/gen_golden.py and tests that are skipped when /root/reference is absent
-may import this file.
+Only oracle/gen_golden.py, tests (skipped when no reference tree is present) and bench.py's
+CPU-baseline leg may import this file.
 """
 import importlib.util
 import io
@@ -16,7 +17,22 @@ import os
 import sys
 import contextlib
 
-REF_ROOT = os.environ.get("STARKS_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _locate():
+  """STARKS_REFERENCE, else the copy staged by baseline/stage_ref.py (the only one that exists on
+  the GPU box), else the authoring container's /root/reference."""
+  env = os.environ.get("STARKS_REFERENCE")
+  if env:
+    return env
+  staged = os.path.join(_REPO, "baseline", "_ref")
+  if os.path.isdir(os.path.join(staged, "starks")):
+    return staged
+  return "/root/reference"
+
+
+REF_ROOT = _locate()
 
 
 def available() -> bool:

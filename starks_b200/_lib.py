@@ -67,7 +67,12 @@ SIGNATURES = {
     "stk_div_linear": (cint, [vp, vp, u64, u32p, u64, vp]),
     "stk_lincomb": (cint, [vp, vp, u64, u64, u64, vp, vp]),
     "stk_trace_generate": (cint, [vp, vp, u64, u64, vp, vp, vp, u64, vp]),
+    "stk_trace_generate_dev": (cint, [vp, vp, u64, u64, u64, vp, vp, vp, u64, vp, u64]),
+    "stk_trace_generate_upload": (cint, [vp, vp, u64, u64, vp, vp, vp, u64, vp, vp, u64]),
+    "stk_count_noncanonical": (cint, [vp, vp, u64, vp, cint]),
     "stk_microbench": (cint, [vp, cint, u64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
+    "stk_microbench_variant": (cint, [vp, cint, cint, u64, ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
 }
 
 

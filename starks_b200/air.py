@@ -1,9 +1,15 @@
 """Trace generation of starks/air.py: get_computational_trace (:31-52) and the witness
-transposition of AIR.generate_witness (:124), through stk_trace_generate.
+transposition of AIR.generate_witness (:124).
 
-The recurrence state[i+1] = step_polys(state[i]) is one sequential 256-bit dependency chain,
-so the library runs it on the calling host thread (Montgomery arithmetic in C++) and writes
-the witness in the ABI's element layout, ready for STARK.mk_proof.
+The recurrence state[i+1] = step_polys(state[i]) is one sequential 256-bit dependency chain.
+  * witness_limbs      one trace on the calling host thread (stk_trace_generate, Montgomery
+                       arithmetic in C++), in the ABI's element layout;
+  * witness_device     traces generated ON THE DEVICE (stk_trace_generate_dev): many independent
+                       traces in parallel, and ONE trace in parallel chunks when the step
+                       polynomials have degree <= 1 (chunk starts from powers of the companion
+                       matrix); a single non-linear trace falls back to the host recurrence
+                       with its upload overlapped (stk_trace_generate_upload).
+Both produce what STARK.mk_proof accepts directly.
 The AIR class itself (asserts steps == 511, sympy) is out of scope."""
 import numpy as np
 
@@ -43,6 +49,41 @@ def witness_limbs(field, inp, steps, width, step_polys, engine=None, out=None):
   eng._check(eng.lib.stk_trace_generate(eng.ctx, h_inp.ctypes.data, steps, width, h_out.ctypes.data,
                                         h_coef.ctypes.data, h_exp.ctypes.data, nm, out.ctypes.data))
   return out
+
+
+def is_affine(step_polys, width, p):
+  """True when every step polynomial has total degree <= 1."""
+  return all(sum(exps) <= 1 for sp in step_polys for exps, _ in monomials_of(sp, width, p))
+
+
+def witness_device(field, inp, steps, width, step_polys, engine=None, ntraces=1, pinned=None):
+  """Trace(s) generated into device memory: returns a DevBuf holding
+  witness[(t*width + dim)*steps + step] (ntraces == 1: the (width, steps) witness mk_proof takes).
+  `inp` is one input state, or a list of `ntraces` input states.
+  One non-linear trace cannot be split: it is generated on the host into `pinned` (a PinnedBuf
+  of shape (width, steps, 8), allocated here when missing) while the finished blocks upload."""
+  eng = engine or default_engine()
+  p = field.p
+  eng.set_field(p)
+  nm, h_out, h_coef, h_exp = _monomial_arrays(step_polys, width, p)
+  states = [inp] if ntraces == 1 and not isinstance(inp[0], (list, tuple)) else list(inp)
+  assert len(states) == ntraces and all(len(s) == width for s in states)
+  h_inp = ints_to_limbs([element_to_int(v) % p for s in states for v in s])
+  d_w = eng.alloc(ntraces * width * steps * 32)
+  if ntraces > 1 or is_affine(step_polys, width, p):
+    eng._check(eng.lib.stk_trace_generate_dev(eng.ctx, h_inp.ctypes.data, ntraces, steps, width, h_out.ctypes.data,
+                                              h_coef.ctypes.data, h_exp.ctypes.data, nm, d_w.ptr, steps))
+  else:
+    own = pinned is None
+    if own:
+      pinned = eng.pinned((width, steps, 8))
+    eng._check(eng.lib.stk_trace_generate_upload(eng.ctx, h_inp.ctypes.data, steps, width, h_out.ctypes.data,
+                                                 h_coef.ctypes.data, h_exp.ctypes.data, nm, pinned.array.ctypes.data,
+                                                 d_w.ptr, steps))
+    if own:
+      eng.sync()
+      pinned.free()
+  return d_w
 
 
 def get_computational_trace(inp, steps, width, step_polys, field=None, engine=None):

@@ -29,6 +29,18 @@ struct stk_ntt_consts {
   uint64_t table_gen = ~0ull;
 };
 
+// (G2^i - 1)^-1 table of the pointwise boundary quotient (stark.cu); per context like `tables`
+struct stk_invtable {
+  stk::fe root;
+  uint64_t n;
+  stk::fe* d;
+};
+
+// Byte budgets of the two table caches (a 2^26 twiddle table is 2 GiB, a 2^23 inverse table
+// 256 MiB): least recently used entries are dropped once a cache would exceed its budget.
+static const uint64_t kTableCacheBytes = 6ull << 30;
+static const uint64_t kInvTableCacheBytes = 2ull << 30;
+
 struct stk_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -39,7 +51,8 @@ struct stk_ctx {
   bool is_stark = true;
   stk::fe p;
   stk::MontField mont;
-  std::vector<stk_table> tables;
+  std::vector<stk_table> tables;       // least recently used first
+  std::vector<stk_invtable> invtables; // least recently used first
   std::vector<stk_ntt_consts> ntt_consts;
   uint64_t table_gen = 0;  // bumped whenever a table is freed
   void* scratch[10] = {};

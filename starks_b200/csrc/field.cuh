@@ -190,7 +190,7 @@ struct StarkField {
     // U = 351*H (9 limbs): even limbs of H give four non-overlapping 41-bit products,
     // the odd ones are accumulated one limb up in a single carry chain.
 #ifdef STK_REDUCE_SPLIT
-    // Measured alternative (tests/gpu_altlib.py): 351*H as two sets of four independent 41-bit
+    // Measured alternative (tools/gpu_altlib.py): 351*H as two sets of four independent 41-bit
     // products (even limbs, odd limbs one up) merged by two add chains -- no accumulating wide
     // multiply, no register-pair realignment moves.  +2 % on the in-register butterfly
     // (87.9 -> 89.7 G/s), nothing on the transform (8.82 vs 8.84 ms): not the default.

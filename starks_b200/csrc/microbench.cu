@@ -2,6 +2,7 @@
 // denominators MEASURED_PEAKS.json does not carry) and in-register throughput of the
 // field multiply / NTT butterfly built from them.
 #include "ctx.h"
+#include "field_exp.cuh"
 
 using namespace stk;
 
@@ -165,5 +166,75 @@ extern "C" __attribute__((visibility("default"))) int stk_microbench(stk_ctx* c,
   if (which == 5) *ops = nthreads * (double)iters * 4.0;
   else if (which == 6) *ops = nthreads * (double)iters * 2.0;
   else *ops = nthreads * (double)iters * ops_per_iter(which);
+  return STK_OK;
+}
+
+// A/B of the experimental multiply (field_exp.cuh) against the production one, in registers:
+// which = 5 (four independent multiplies per iteration) or 6 (two DIF butterflies); variant 0 is
+// the production StarkField, bit 0 = accumulators without zero-initialisation, bit 1 = aligned
+// 351*H rows.  *mismatches = how many of the kernel's outputs differ from the production
+// kernel's on the same inputs (must be 0: both are exact).
+template <int V>
+static int run_variant(stk_ctx* c, int which, uint64_t iters, unsigned blocks, unsigned threads, fe* out, const fe* in) {
+  if (which == 5) field_kernel<StarkFieldX<V>, 5><<<blocks, threads, 0, c->stream>>>(out, in, iters, StarkFieldX<V>());
+  else field_kernel<StarkFieldX<V>, 6><<<blocks, threads, 0, c->stream>>>(out, in, iters, StarkFieldX<V>());
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int stk_microbench_variant(stk_ctx* c, int variant, int which, uint64_t iters, float* ms,
+                                                                              double* ops, uint64_t* mismatches) {
+  if (!c || !ms || !ops || !mismatches || (which != 5 && which != 6) || variant < 0 || variant > 3) return STK_EINVAL;
+  if (!c->is_stark) return stk_fail(c, STK_EUNSUPPORTED, "the experimental multiply is for the STARK prime");
+  const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+  const uint64_t nthr = (uint64_t)blocks * threads;
+  void* buf;
+  STK_TRY(stk_scratch(c, 2, (2 * nthr + 1024) * sizeof(fe), &buf));
+  fe* out = (fe*)buf;
+  fe* ref = out + nthr;
+  fe* in = ref + nthr;
+  std::vector<fe> h(1024);
+  for (int i = 0; i < 1024; ++i)
+    for (int l = 0; l < 8; ++l) h[i].v[l] = (uint32_t)(2654435761u * (i * 8 + l + 1)) & (l == 7 ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+  // a few saturated operands so that the carry limbs of every row are exercised
+  for (int l = 0; l < 8; ++l) { h[5].v[l] = 0xFFFFFFFFu; h[6].v[l] = l == 0 ? 0u : (l == 1 ? 0xFFFFFEA1u : 0xFFFFFFFFu); }
+  h[5] = StarkField().reduce(h[5]);
+  STK_CUDA(c, cudaMemcpyAsync(in, h.data(), 1024 * sizeof(fe), cudaMemcpyHostToDevice, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  const uint64_t check_iters = iters < 64 ? iters : 64;
+  if (which == 5) field_kernel<StarkField, 5><<<blocks, threads, 0, c->stream>>>(ref, in, check_iters, StarkField());
+  else field_kernel<StarkField, 6><<<blocks, threads, 0, c->stream>>>(ref, in, check_iters, StarkField());
+  STK_CUDA(c, cudaGetLastError());
+#define RUNV(IT) \
+  do { \
+    switch (variant) { \
+      case 0: STK_TRY(run_variant<0>(c, which, IT, blocks, threads, out, in)); break; \
+      case 1: STK_TRY(run_variant<1>(c, which, IT, blocks, threads, out, in)); break; \
+      case 2: STK_TRY(run_variant<2>(c, which, IT, blocks, threads, out, in)); break; \
+      default: STK_TRY(run_variant<3>(c, which, IT, blocks, threads, out, in)); break; \
+    } \
+  } while (0)
+  RUNV(check_iters);
+  std::vector<fe> ho(nthr), hr(nthr);
+  STK_CUDA(c, cudaMemcpyAsync(ho.data(), out, nthr * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+  STK_CUDA(c, cudaMemcpyAsync(hr.data(), ref, nthr * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+  STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint64_t bad = 0;
+  for (uint64_t i = 0; i < nthr; ++i) bad += fe_eq(ho[i], hr[i]) ? 0 : 1;
+  *mismatches = bad;
+  cudaEvent_t e0, e1;
+  STK_CUDA(c, cudaEventCreate(&e0));
+  STK_CUDA(c, cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; ++rep) {
+    STK_CUDA(c, cudaEventRecord(e0, c->stream));
+    RUNV(iters);
+    STK_CUDA(c, cudaEventRecord(e1, c->stream));
+    STK_CUDA(c, cudaEventSynchronize(e1));
+  }
+#undef RUNV
+  STK_CUDA(c, cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ops = (double)nthr * (double)iters * (which == 5 ? 4.0 : 2.0);
   return STK_OK;
 }

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t sm_phys(uint32_t pos) { return pos ^ ((pos >
 // on load, real input column = virtual >> cshift; also the interleaved store, for single-pass
 // coset transforms); 2 = final pass of a coset transform (interleaved store only).  The plain
 // instantiation carries none of this: even a few extra integer instructions in its load / store
-// paths cost 2 % on the 64 x 2^20 transform (measured, tests/gpu_altlib.py).
+// paths cost 2 % on the 64 x 2^20 transform (measured, tools/gpu_altlib.py).
 template <class F, int R, int ZS, bool TRIV>
 __device__ __forceinline__ void ntt_round(const NttPass& A, const F& f, uint32_t* sm, uint32_t T,
                                           uint32_t Jcta, uint32_t col0, int a, bool first, bool last) {

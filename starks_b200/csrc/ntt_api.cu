@@ -100,6 +100,7 @@ extern "C" __attribute__((visibility("default"))) int stk_field_set(stk_ctx* c, 
   STK_CUDA(c, cudaStreamSynchronize(c->stream));
   for (auto& t : c->tables) cudaFree(t.d);
   c->tables.clear();
+  stk_stark_release(c);   // the inverse tables are per field too
   c->ntt_consts.clear();
   ++c->table_gen;
   if (host::is_stark_prime(p)) {
@@ -162,11 +163,32 @@ extern "C" __attribute__((visibility("default"))) int stk_memset(stk_ctx* c, voi
 
 // ------------------------------------------------------------------ twiddle tables
 
+// Cache discipline: `tables` is kept least-recently-used first; a hit moves its entry to the
+// back.  An insertion evicts from the front while the cache holds 48 entries or more than
+// kTableCacheBytes, but never the most recently used entry -- so a caller may hold the pointer
+// of ONE earlier lookup across the next lookup (stk_div_linear holds r's table while fetching
+// r^-1's).
+static void table_touch(stk_ctx* c, size_t i) {
+  if (i + 1 == c->tables.size()) return;
+  stk_table t = c->tables[i];
+  c->tables.erase(c->tables.begin() + i);
+  c->tables.push_back(t);
+}
+
 int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
-  for (auto& t : c->tables)
-    if (t.n == n && fe_eq(t.root, root)) { *d_table = t.d; return STK_OK; }
-  if (c->tables.size() >= 48) {  // bounded cache: drop the oldest
-    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->tables.size(); ++i)
+    if (c->tables[i].n == n && fe_eq(c->tables[i].root, root)) {
+      *d_table = c->tables[i].d;
+      table_touch(c, i);
+      return STK_OK;
+    }
+  const uint64_t need = std::max<uint64_t>(n, 1) * sizeof(fe);
+  uint64_t held = 0;
+  for (auto& t : c->tables) held += std::max<uint64_t>(t.n, 1) * sizeof(fe);
+  bool synced = false;
+  while (c->tables.size() > 1 && (c->tables.size() >= 48 || held + need > kTableCacheBytes)) {
+    if (!synced) { STK_CUDA(c, cudaStreamSynchronize(c->stream)); synced = true; }
+    held -= std::max<uint64_t>(c->tables.front().n, 1) * sizeof(fe);
     cudaFree(c->tables.front().d);
     c->tables.erase(c->tables.begin());
     ++c->table_gen;
@@ -193,12 +215,22 @@ int stk_get_table(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table) {
 
 int stk_get_table_strided(stk_ctx* c, const fe& root, uint64_t n, const fe** d_table, uint64_t* stride) {
   *stride = 1;
-  for (auto& t : c->tables)
-    if (t.n == n && fe_eq(t.root, root)) { *d_table = t.d; return STK_OK; }
-  for (auto& t : c->tables) {
+  for (size_t i = 0; i < c->tables.size(); ++i)
+    if (c->tables[i].n == n && fe_eq(c->tables[i].root, root)) {
+      *d_table = c->tables[i].d;
+      table_touch(c, i);
+      return STK_OK;
+    }
+  for (size_t i = 0; i < c->tables.size(); ++i) {
+    const stk_table& t = c->tables[i];
     if (t.n > n && t.n % n == 0) {
       uint64_t s = t.n / n;
-      if (fe_eq(stk_h_pow(c, t.root, s), root)) { *d_table = t.d; *stride = s; return STK_OK; }
+      if (fe_eq(stk_h_pow(c, t.root, s), root)) {
+        *d_table = t.d;
+        *stride = s;
+        table_touch(c, i);
+        return STK_OK;
+      }
     }
   }
   return stk_get_table(c, root, n, d_table);
@@ -211,7 +243,7 @@ static int ilog2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) ++l; retur
 static int ntt_max_radix() { return 3; }  // radix-4 measured no faster: profiles/r01_ntt_radix_sweep.txt
 
 // Rounds of a pass.  Where the remainder round (k mod R levels) goes was measured
-// (tests/gpu_knobs.py, profiles/r01_ntt_round_order.txt): last in non-final passes and in
+// (tools/gpu_knobs.py, profiles/r01_ntt_round_order.txt): last in non-final passes and in
 // 1024-element final passes, first in 2048-element final passes; the spread is 1-3 %.
 static void fill_rounds(NttPass& P, int R) {
   int k = P.k, rem = k % R, full = k / R, idx = 0;
@@ -322,6 +354,16 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
   if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
                                 (unsigned long long)n_in, (unsigned long long)n);
   if (n > (1ull << 30)) return stk_fail(c, STK_EUNSUPPORTED, "transform length above 2^30");
+  // multi-pass launches put the column index in gridDim.y (<= 65535): wider batches run as
+  // consecutive column groups on the same stream (the scratch buffer is reused in stream order)
+  if (batch > 32768 && n > 2048 && !peer && !hash_nodes) {
+    for (uint64_t b0 = 0; b0 < batch; b0 += 32768) {
+      const uint64_t nb = std::min<uint64_t>(32768, batch - b0);
+      STK_TRY(ntt_dev_on(c, s, scratch_slot, d_in + b0 * in_stride, n_in, in_stride, d_out + b0 * out_stride,
+                         out_stride, n, nb, root, inverse, scale, nullptr, nullptr));
+    }
+    return STK_OK;
+  }
   stk_ntt_consts* K = nullptr;
   for (auto& e : c->ntt_consts)
     if (e.n == n && e.inverse == (inverse ? 1 : 0) && fe_eq(e.root, root)) { K = &e; break; }

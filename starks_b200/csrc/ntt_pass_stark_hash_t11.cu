@@ -11,11 +11,11 @@ using namespace stk;
 
 template <int MAXT, int MINB>
 static int launch_hash_pass(stk_ctx* c, cudaStream_t s, const NttPass& P) {
-  static bool attr_done = false;
+  static bool attr_done[64] = {};  // cudaFuncSetAttribute is per device
   auto kern = ntt_pass_kernel<StarkField, 3, MAXT, MINB, false, true>;
-  if (!attr_done) {
+  if (!attr_done[c->device & 63]) {
     STK_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 8 * MAXT));
-    attr_done = true;
+    attr_done[c->device & 63] = true;
   }
   const uint32_t T = 1u << P.logT;
   if (T > 8u * MAXT) return stk_fail(c, STK_EUNSUPPORTED, "tile larger than this instantiation");

@@ -8,11 +8,11 @@ using namespace stk;
 
 template <class F, int MAXR, int MAXT, int MINB, int ZS>
 static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& f) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // cudaFuncSetAttribute is per device
+  if (!attr_done[c->device & 63]) {
     STK_CUDA(c, cudaFuncSetAttribute(ntt_pass_kernel<F, MAXR, MAXT, MINB, ZS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 8 * MAXT));
-    attr_done = true;
+    attr_done[c->device & 63] = true;
   }
   const uint32_t T = 1u << P.logT;
   if ((1u << P.logT) > 8u * MAXT) return stk_fail(c, STK_EUNSUPPORTED, "tile larger than this instantiation");

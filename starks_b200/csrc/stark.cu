@@ -414,15 +414,9 @@ STK_API int stk_quotient_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uin
 // (STARK prime only): d_bev[j][i] = (P_j(x_i) - (i0_j + i1_j x_i)) / ((x_i - 1)(x_i - last)) with
 // last = g2^last_index (a multiple of ext), pointwise wherever the denominator is non-zero; the
 // values at i = 0 mod ext come from d_bsub = B_j on <g2^ext> (transform of B's coefficients).
-namespace {
-struct InvTable { stk_ctx* c; fe root; uint64_t n; fe* d; };
-std::vector<InvTable> g_invtables;
-}  // namespace
 void stk_stark_release(stk_ctx* c) {
-  for (size_t i = 0; i < g_invtables.size();) {
-    if (g_invtables[i].c == c) { cudaFree(g_invtables[i].d); g_invtables.erase(g_invtables.begin() + i); }
-    else ++i;
-  }
+  for (auto& t : c->invtables) cudaFree(t.d);
+  c->invtables.clear();
 }
 STK_API int stk_boundary_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uint64_t ext, uint64_t width,
                               uint64_t col_stride, const uint32_t g2[8], uint64_t last_index, const uint32_t* h_interp,
@@ -442,16 +436,32 @@ STK_API int stk_boundary_eval(stk_ctx* c, const uint32_t* d_pev, uint64_t n, uin
   int xshift = 0;
   while ((1ull << xshift) < xs) ++xshift;
   if ((1ull << xshift) != xs) { STK_TRY(stk_get_table(c, G2, n, &X)); xshift = 0; }
+  // per-context cache (least recently used first), bounded by kInvTableCacheBytes; only this
+  // context's own stream can still be reading an evicted table, and it is synchronised first
   fe* T = nullptr;
-  for (auto& t : g_invtables)
-    if (t.c == c && t.n == n && fe_eq(t.root, G2)) T = t.d;
+  for (size_t i = 0; i < c->invtables.size(); ++i)
+    if (c->invtables[i].n == n && fe_eq(c->invtables[i].root, G2)) {
+      stk_invtable t = c->invtables[i];
+      c->invtables.erase(c->invtables.begin() + i);
+      c->invtables.push_back(t);
+      T = t.d;
+      break;
+    }
   if (!T) {
-    if (g_invtables.size() >= 8) { STK_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(g_invtables.front().d); g_invtables.erase(g_invtables.begin()); }
+    uint64_t held = 0;
+    for (auto& t : c->invtables) held += t.n * sizeof(fe);
+    bool synced = false;
+    while (!c->invtables.empty() && (c->invtables.size() >= 8 || held + n * sizeof(fe) > kInvTableCacheBytes)) {
+      if (!synced) { STK_CUDA(c, cudaStreamSynchronize(c->stream)); synced = true; }
+      held -= c->invtables.front().n * sizeof(fe);
+      cudaFree(c->invtables.front().d);
+      c->invtables.erase(c->invtables.begin());
+    }
     STK_CUDA(c, cudaMalloc(&T, n * sizeof(fe)));
     const uint64_t chunks = (n + kInvChunk - 1) / kInvChunk;
     invtable_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, c->stream>>>(X, xshift, n, T);
     STK_CUDA(c, cudaGetLastError());
-    g_invtables.push_back({c, G2, n, T});
+    c->invtables.push_back({G2, n, T});
   }
   BoundaryInterp I;
   for (uint64_t j = 0; j < 12; ++j) {

@@ -103,6 +103,7 @@ class Engine:
     self.device = device
     self.p = P_STARK
     self._pool = {}
+    self._flag = None   # one pinned word for asynchronous device-side checks
 
   def release_pool(self):
     """Returns pooled device buffers to the driver."""
@@ -253,10 +254,21 @@ class Engine:
     if k == 0:
       return []
     depth = len(branches[0]) - 1
+    assert depth >= 1, "malformed branch"
     n = 1 << depth
     L = len(branches[0][0])
     rec = 2 * L + 32 * (depth - 1)
-    assert all(len(b) == depth + 1 for b in branches), "branches of one tree have one length"
+    # The kernel hashes fixed offsets of the packed record ([0:L] leaf, [L:2L] sibling leaf, then
+    # 32-byte nodes) and the caller computes with b[0]: every element must have exactly the width
+    # the kernel assumes, otherwise a proof could shift bytes between elements and have a value
+    # other than the committed leaf accepted (the reference hashes exactly the proof[0] it
+    # returns, merkle_tree.py:71-86).
+    assert L > 0 and L % 32 == 0, "malformed branch: leaf width"
+    for b in branches:
+      assert len(b) == depth + 1, "branches of one tree have one length"
+      assert len(b[0]) == L and len(b[1]) == L, "malformed branch: leaf / sibling width"
+      for x in b[2:]:
+        assert len(x) == 32, "malformed branch: node width"
     buf = np.frombuffer(b"".join(b"".join(b) for b in branches), dtype=np.uint8)
     assert buf.size == k * rec, "malformed branch"
     idx = np.asarray(indices, dtype=np.uint64)
@@ -302,6 +314,24 @@ class Engine:
       proof.append([root2, [[col[i]] + rows[4 * i:4 * i + 4] for i in range(k)]])
     proof.append(list(struct.unpack("32s" * nn, buf[off:off + 32 * nn])))
     return proof
+
+  def count_noncanonical(self, d_vals, n, wait=True):
+    """How many of the n elements at d_vals are >= p (stk_count_noncanonical).  wait=False
+    returns a zero-argument callable to be called after the stream has been synchronised."""
+    if wait:
+      bad = ctypes.c_uint32(0)
+      self._check(self.lib.stk_count_noncanonical(self.ctx, d_vals, n, ctypes.addressof(bad), 1))
+      return bad.value
+    if self._flag is None:
+      self._flag = self.pinned((16,))
+    self._check(self.lib.stk_count_noncanonical(self.ctx, d_vals, n, self._flag.ptr, 0))
+    return lambda: int(self._flag.array[0])
+
+  def microbench_variant(self, variant, which, iters):
+    ms, ops, bad = ctypes.c_float(), ctypes.c_double(), ctypes.c_uint64()
+    self._check(self.lib.stk_microbench_variant(self.ctx, variant, which, iters, ctypes.byref(ms), ctypes.byref(ops),
+                                                ctypes.byref(bad)))
+    return ms.value, ops.value, bad.value
 
   def microbench(self, which, iters):
     ms, ops = ctypes.c_float(), ctypes.c_double()

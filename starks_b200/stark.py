@@ -77,7 +77,12 @@ class STARK(object):
 
   # ----------------------------------------------------------------- prover
   def _witness_limbs(self, witness):
+    """-> (width, steps, 8) uint32 host array, or the device buffer itself when the witness is
+    already on the device (DevBuf from air.witness_device / stk_trace_generate_dev)."""
     p = self.field.p
+    if hasattr(witness, "ptr") and hasattr(witness, "nbytes"):
+      assert witness.nbytes >= self.width * self.steps * 32
+      return witness
     if isinstance(witness, np.ndarray):
       assert witness.shape == (self.width, self.steps, 8)
       return np.ascontiguousarray(witness, dtype=np.uint32)
@@ -95,9 +100,19 @@ class STARK(object):
     w, steps, ext, N = self.width, self.steps, self.extension_factor, self.precision
     G2, last = int(self.G2), int(self.last_step_position)
     tr = self._witness_limbs(witness)
-    assert tr.shape[1] == steps
     E = 32
-    d_trace = eng.alloc(w * steps * E).upload(tr, wait=False)   # `tr` lives until the syncs below
+    on_device = not isinstance(tr, np.ndarray)
+    if on_device:
+      d_trace = tr
+    else:
+      assert tr.shape[1] == steps
+      d_trace = eng.alloc(w * steps * E).upload(tr, wait=False)   # `tr` lives until the syncs below
+    if on_device or isinstance(witness, np.ndarray):
+      # caller-supplied limbs are used as they are: the kernels' add/sub/reduce assume canonical
+      # residues (the list path reduces mod p like IntegerModP.__init__, modp.py:35-36)
+      noncanonical = eng.count_noncanonical(d_trace.ptr, w * steps, wait=False)
+    else:
+      noncanonical = None
     d_cols = eng.alloc(3 * w * N * E)        # rows: P_1..P_w, D_1..D_w, B_1..B_w (stark.py:247)
     d_t1 = eng.alloc(w * N * E)
     d_t2 = eng.alloc(w * N * E)
@@ -154,6 +169,10 @@ class STARK(object):
       dst = d_coef.at((w + j) * cs * E) if merged else d_t1.at(j * M * E)
       eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t2.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
                                         dst, ctypes.byref(bad)))
+      if noncanonical is not None:   # stk_quotient_z synchronised the stream: the count is in
+        if noncanonical():
+          raise ValueError("witness holds elements >= p; reduce them mod p first")
+        noncanonical = None
       assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
     if pointwise_d:
       # D on <G_M> (contains <G1>, where Z vanishes) from its coefficients, everything else pointwise
@@ -165,7 +184,11 @@ class STARK(object):
     elif not merged:
       eng.ntt(d_t1.ptr, M, M, d_cols.at(w * N * E), N, N, w, G2)
     # construct_boundary_polynomials (:80-104): B = (P - I) / ((X - 1)(X - last))
-    out_vals = limbs_to_ints(tr[:, -1, :])
+    if on_device:
+      last_rows = np.stack([d_trace.download((1, 8), byte_offset=(j * steps + steps - 1) * E)[0] for j in range(w)])
+    else:
+      last_rows = tr[:, -1, :]
+    out_vals = limbs_to_ints(last_rows)
     one_l = int_to_limbs(1)
     interps = []
     for j in range(w):
@@ -238,7 +261,7 @@ class STARK(object):
     if keep_device:
       self.device = dict(cols=d_cols, pcoef=d_coef, l=d_l, mnodes=d_mnodes, lnodes=d_lnodes)
     else:
-      for b in (d_trace, d_coef, d_i, d_cols, d_t1, d_t2, d_mnodes, d_l, d_lnodes):
+      for b in (d_coef, d_i, d_cols, d_t1, d_t2, d_mnodes, d_l, d_lnodes) + (() if on_device else (d_trace,)):
         b.free()
     return proof
 
@@ -300,7 +323,9 @@ class STARK(object):
     zeropoly2_x = (x - 1) * (x - last) % p
     for dim in range(width):                                             # boundary constraints
       (_, _, input_value) = boundary[dim]
-      if isinstance(witness, np.ndarray):
+      if hasattr(witness, "ptr") and hasattr(witness, "download"):
+        output_dim = limbs_to_ints(witness.download((1, 8), byte_offset=(dim * self.steps + self.steps - 1) * 32))[0]
+      elif isinstance(witness, np.ndarray):
         output_dim = limbs_to_ints(witness[dim, -1:, :])[0]
       else:
         output_dim = element_to_int(witness[dim][-1]) % p

@@ -2,7 +2,7 @@
 another on cuda:0 (no kernel waits on another), the all-to-all is a host-side regrouping of
 the ranks' buffers.  Checks stk_ntt_dist_phase (four-step NTT) and the sharded Merkle commit
 geometry against the single-GPU transform / tree.  The NCCL path itself is exercised by
-tests/gpu_dist_check.py under torchrun (profiles/r01_dist_*gpu.txt) and the index logic by
+tools/gpu_dist_check.py under torchrun (profiles/r01_dist_*gpu.txt) and the index logic by
 tests/test_dist_gloo.py on CPU."""
 import numpy as np
 import pytest

@@ -123,20 +123,27 @@ def test_install_rebinds_reference_when_present():
     pytest.skip("upstream reference tree not present")
   pyref.load()
   import starks.stark, starks.fft, starks.merkle_tree, starks.fri
-  saved = {m: dict(vars(sys.modules[m])) for m in ("starks.fft", "starks.merkle_tree", "starks.fri", "starks.stark", "starks.utils")}
+  before = {m: dict(vars(sys.modules[m])) for m in ("starks.fft", "starks.merkle_tree", "starks.fri", "starks.stark", "starks.utils")}
   saved_mk = starks.stark.STARK.mk_proof
+  import starks_b200.install as shim
+  import starks_b200.fft as bfft, starks_b200.merkle_tree as bmt, starks_b200.fri as bfri
   try:
-    import starks_b200.install as shim
-    import starks_b200.fft as bfft, starks_b200.merkle_tree as bmt, starks_b200.fri as bfri
     assert shim.install()
     assert starks.fft.fft_1d is bfft.fft_1d and starks.merkle_tree.merkelize is bmt.merkelize
     assert starks.stark.merkelize is bmt.merkelize and starks.stark.FRI is bfri.FRI
     assert starks.fri.merkelize is bmt.merkelize and starks.fri.SmoothSubgroupFRI is bfri.SmoothSubgroupFRI
     assert starks.stark.STARK.mk_proof is not saved_mk
+    # function-level mode: the upstream prover body stays, only its callees are rebound
+    assert shim.install(replace_prover=False)
+    assert starks.stark.STARK.mk_proof is saved_mk and starks.stark.merkelize is bmt.merkelize
   finally:
-    for m, d in saved.items():
-      vars(sys.modules[m]).update(d)
-    starks.stark.STARK.mk_proof = saved_mk
+    shim.uninstall()
+  assert not shim.installed()
+  assert starks.stark.STARK.mk_proof is saved_mk
+  for m, d in before.items():
+    now = vars(sys.modules[m])
+    for k, v in d.items():
+      assert now.get(k) is v, (m, k)
 
 
 def test_compression_mirror(oracle):

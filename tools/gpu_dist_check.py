@@ -1,5 +1,5 @@
 """Multi-GPU check + timing (run under torchrun on N GPUs of one box):
-   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/gpu_dist_check.py
+   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/gpu_dist_check.py
 Parity: dist_ntt vs the single-GPU transform; sharded LDE+commit root vs single-GPU root.
 Timing: BASELINE config 3 (64 columns x 2^18 -> 2^21, columns sharded) and config 4
 (one 2^26-point NTT, four-step)."""

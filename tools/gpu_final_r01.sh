@@ -13,7 +13,7 @@ echo "ntt full rc=$?"
 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:merkle_leaf_pairs_cols -s 2 -c 1 -o gpurun_out/prof_merkle_r01 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full2.log 2>&1
 echo "merkle full rc=$?"
-python tests/gpu_profile_proof.py > gpurun_out/proof_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_proof_r01.csv python tests/gpu_profile_proof.py > gpurun_out/ncu_proof.log 2>&1
+python tools/gpu_profile_proof.py > gpurun_out/proof_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_proof_r01.csv python tools/gpu_profile_proof.py > gpurun_out/ncu_proof.log 2>&1
 echo "proof list rc=$?"; cat gpurun_out/proof_plain.log | tail -1
 cat gpurun_out/bench_r01.json

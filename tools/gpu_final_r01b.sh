@@ -12,7 +12,7 @@ echo "launch list rc=$?"
 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ntt_pass -s 6 -c 2 -o gpurun_out/prof_ntt_r01b python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
 echo "ntt full rc=$?"
-python tests/gpu_profile_proof.py > gpurun_out/proof_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_proof_r01b.csv python tests/gpu_profile_proof.py > gpurun_out/ncu_proof.log 2>&1
+python tools/gpu_profile_proof.py > gpurun_out/proof_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_proof_r01b.csv python tools/gpu_profile_proof.py > gpurun_out/ncu_proof.log 2>&1
 echo "proof list rc=$?"; tail -1 gpurun_out/proof_plain.log
 cat gpurun_out/bench_r01b.json
