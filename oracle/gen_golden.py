@@ -1,7 +1,7 @@
 """Generates tests/golden/*.json by running the UNMODIFIED upstream Python reference
 (/root/reference, with the App. B FRI restoration applied in memory by pyref.py).
 
-Run in the authoring container only:   python oracle/gen_golden.py [--big]
+Run in the authoring container only:   python oracle/gen_golden.py [--big | --degrees]
 The reference tree does not travel to the GPU box; the JSON fixtures do.
 Inputs use the synthetic generator of SURVEY.md 8(d):
   synth(col, i) = int(blake2s(le32(col) || le64(i))) mod p ;  w_N = 7^((p-1)/N).
@@ -57,6 +57,9 @@ def shape(x):
 
 def main():
   big = "--big" in sys.argv
+  degrees = "--degrees" in sys.argv   # only tests/golden/stark_degrees.json (everything else untouched)
+  import tempfile
+  OUTX = tempfile.mkdtemp() if degrees else OUT
   st = pyref.load()
   from starks.modp import IntegersModP
   from starks.polynomial import polynomials_over
@@ -100,7 +103,7 @@ def main():
   g["blake_abc"] = blake(b"abc").hex()
   g["blake_lens"] = [{"len": n, "digest": blake(bytes((i * 7 + 3) & 255 for i in range(n))).hex()}
                      for n in (0, 1, 32, 63, 64, 65, 128, 192, 384, 2048, 4096)]
-  json.dump(g, open(os.path.join(OUT, "field_utils.json"), "w"), indent=1)
+  json.dump(g, open(os.path.join(OUTX, "field_utils.json"), "w"), indent=1)
 
   # ---------------------------------------------------------------------------- fft
   g = {"cases": []}
@@ -145,7 +148,7 @@ def main():
   prod = mul_polys(a, a, r512)
   g["mul_polys_512"] = {"root": hx(int(r512)), "a": [0, 1, 2, 3], "H": H([int(x) for x in prod]),
                         "first": [hx(int(x)) for x in prod[:8]]}
-  json.dump(g, open(os.path.join(OUT, "fft.json"), "w"), indent=1)
+  json.dump(g, open(os.path.join(OUTX, "fft.json"), "w"), indent=1)
 
   # ------------------------------------------------------------------------- merkle
   g = {"trees": []}
@@ -184,7 +187,7 @@ def main():
                      "H_cols": [H([int(x) for x in e]) for e in evs],
                      "branch5": [b.hex() for b in mk_branch(mt, 5)],
                      "tree_digest": hashlib.blake2s(b"".join(mt)).hexdigest()}
-  json.dump(g, open(os.path.join(OUT, "merkle.json"), "w"), indent=1)
+  json.dump(g, open(os.path.join(OUTX, "merkle.json"), "w"), indent=1)
 
   # ---------------------------------------------------------------------------- fri
   g = {}
@@ -216,7 +219,7 @@ def main():
                         "final_len": len(prf[-1][0]) if False else len(prf[-1]),
                         "digest": proof_digest(prf)})
     print("fri 2^%d: %.2fs" % (logn, time.time() - t0))
-  json.dump(g, open(os.path.join(OUT, "fri.json"), "w"), indent=1)
+  json.dump(g, open(os.path.join(OUTX, "fri.json"), "w"), indent=1)
 
   # -------------------------------------------------------------------------- stark
   g = {"proofs": []}
@@ -258,6 +261,22 @@ def main():
       [{"1,0,0,0,0,0": 1}, {"0,1,0,0,0,0": 1}, {"0,0,1,0,0,0": 1}, {"0,0,0,1,0,0": 1}, {"0,0,0,0,1,0": 1},
        {"1,1,1,1,1,1": 1}])
   run("fib256", 2, 256, [0, 1], fib, fib_desc)
+  if degrees:
+    # constraint degrees the other files do not reach (they hold 1, 2, 3, 6): 4, 5, 7 and 8 = the
+    # extension factor, the largest the reference's domain supports (deg C < N), in the style of
+    # the commented starks/test/test_stark.py:268-350 (cubic "MiMC-like", varying quintic)
+    g = {"proofs": []}
+    run("deg4_8", 2, 8, [2, 5], lambda X: [X[0], X[0] + X[1]**4], [{"1,0": 1}, {"1,0": 1, "0,4": 1}])
+    run("deg5_16", 2, 16, [3, 2], lambda X: [X[1], X[0] + X[1]**5], [{"0,1": 1}, {"1,0": 1, "0,5": 1}])
+    run("deg7_8", 2, 8, [2, 3], lambda X: [X[0], X[0] + 2 * X[1]**7], [{"1,0": 1}, {"1,0": 1, "0,7": 2}])
+    run("deg8_8", 2, 8, [5, 2], lambda X: [X[0], 3 * X[0] + X[1]**8], [{"1,0": 1}, {"1,0": 3, "0,8": 1}])
+    run("deg8_32", 2, 32, [5, 2], lambda X: [X[1], 3 * X[0] + X[1]**8], [{"0,1": 1}, {"1,0": 3, "0,8": 1}])
+    run("w4_mixed_16", 4, 16, [1, 2, 3, 4],
+        lambda X: [X[1], X[2] * X[3], X[0]**2 * X[1]**2 + X[3], X[0] + X[1] * X[2] * X[3]**3],
+        [{"0,1,0,0": 1}, {"0,0,1,1": 1}, {"2,2,0,0": 1, "0,0,0,1": 1}, {"1,0,0,0": 1, "0,1,1,3": 1}])
+    json.dump(g, open(os.path.join(OUT, "stark_degrees.json"), "w"), indent=1)
+    print("golden vectors written to", OUT)
+    return
   if big:
     run("fib1024", 2, 1024, [0, 1], fib, fib_desc)
   json.dump(g, open(os.path.join(OUT, "stark.json" if not big else "stark_big.json"), "w"), indent=1)

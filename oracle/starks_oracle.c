@@ -623,7 +623,11 @@ EXPORT int orc_poly_divmod(const uint32_t *p, const uint32_t *a, uint64_t na, co
 EXPORT int orc_poly_eval(const uint32_t *p, const uint32_t *a, uint64_t na, const uint32_t *x,
                          uint64_t nx, uint32_t *out) {
   field_t F; if (field_init(&F, p)) return -1;
-  for (uint64_t k = 0; k < nx; ++k) {
+  /* the points are independent: spread them over the host threads when the polynomial is long */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) if (na * nx > (1u << 22))
+#endif
+  for (int64_t k = 0; k < (int64_t)nx; ++k) {
     fe xv, xm, acc = {{0, 0, 0, 0}};
     fe_load(&xv, x + 8 * k); f_reduce(&F, &xv, &xv); f_to_mont(&F, &xm, &xv);
     for (uint64_t i = na; i-- > 0;) {

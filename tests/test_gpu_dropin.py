@@ -125,7 +125,7 @@ def test_fri_vs_oracle_larger(mods, oracle):
 # ---- STARK (commented starks/test/test_stark.py:215-350) -------------------------------
 def _golden_proofs():
   out = {}
-  for name in ("stark.json", "stark_big.json"):
+  for name in ("stark.json", "stark_big.json", "stark_degrees.json"):
     try:
       for e in load_golden(name)["proofs"]:
         out[e["tag"]] = e
@@ -152,7 +152,8 @@ def _step_polys(mods, F, e):
   return polys
 
 
-@pytest.mark.parametrize("tag", ["fib8", "fib32", "cubic8", "affine32", "w3_8", "w6_8", "quad128", "fib256", "fib1024"])
+@pytest.mark.parametrize("tag", ["fib8", "fib32", "cubic8", "affine32", "w3_8", "w6_8", "quad128", "fib256", "fib1024",
+                                 "deg4_8", "deg5_16", "deg7_8", "deg8_8", "deg8_32", "w4_mixed_16"])
 def test_stark_proofs_golden(mods, oracle, tag):
   g = _golden_proofs()
   if tag not in g:

@@ -192,3 +192,23 @@ def test_verifier_closed_forms_equal_lagrange_interpolation():
   ws = _interp_weights(xs, 97)
   for x in range(97):
     assert _weighted_eval(xs, ws, ys, x, 97) == _lagrange_eval(xs, ys, x, 97)
+
+
+def test_opened_value_checker_accepts_oracle_proofs(oracle):
+  """tests/proofcheck.py (used on the GPU at 2^20 steps) against oracle-made proofs: it accepts
+  them, and it notices a wrong linear combination -- which upstream's verifier would not
+  (starks/stark.py:374-381 is commented out)."""
+  from proofcheck import check_opened_values
+  import numpy as np
+  for steps, inp, sp in ((256, [0, 1], [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]),
+                         (64, [2, 3], [{(0, 1): 1}, {(1, 0): 1, (0, 2): 1}])):
+    wit = oracle.computational_trace(P, inp, steps, sp)
+    proof = oracle.StarkOracle(steps, 8, 2, sp).mk_proof(wit, [(0, 0, inp[0]), (0, 1, inp[1])])
+    limbs = np.stack([oracle.to_limbs(col) for col in wit])
+    assert check_opened_values(oracle, proof, limbs, inp, steps, 8, sp) == 80
+  # a proof whose l-tree opens something else at one position
+  bad = [proof[0], proof[1], [list(b) for b in proof[2]], proof[3]]
+  other = proof[2][5]
+  bad[2][2] = list(other)
+  with pytest.raises(AssertionError):
+    check_opened_values(oracle, bad, limbs, inp, steps, 8, sp)

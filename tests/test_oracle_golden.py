@@ -193,9 +193,10 @@ def _step_polys(desc):
   return [{tuple(int(t) for t in k.split(",")): v for k, v in sp.items()} for sp in desc]
 
 
-@pytest.mark.parametrize("tag", ["fib8", "fib32", "cubic8", "affine32", "w3_8", "w6_8", "quad128", "fib256"])
+@pytest.mark.parametrize("tag", ["fib8", "fib32", "cubic8", "affine32", "w3_8", "w6_8", "quad128", "fib256",
+                                 "deg4_8", "deg5_16", "deg7_8", "deg8_8", "deg8_32", "w4_mixed_16"])
 def test_stark_proofs(oracle, tag):
-  g = {e["tag"]: e for e in load_golden("stark.json")["proofs"]}
+  g = {e["tag"]: e for name in ("stark.json", "stark_degrees.json") for e in load_golden(name)["proofs"]}
   e = g[tag]
   sp = _step_polys(e["step_polys"])
   S = oracle.StarkOracle(e["steps"], e["ext"], e["width"], sp)
