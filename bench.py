@@ -528,6 +528,54 @@ def section_config5(cx, line):
   line["stark_proof"] = out
 
 
+def section_config5_sharded(cx, line, reps=3):
+  """ONE proof over the N GPUs of this run (dist.ShardedProver) next to the same proof on one GPU:
+  the Fibonacci AIR of config 5 (w = 2: six committed columns, little to shard) and an 8-wide affine
+  AIR (24 committed columns over a 2^21-point domain), where the column split has something to divide."""
+  torch, eng, world, rank, dev = cx.torch, cx.eng, cx.world, cx.rank, cx.dev
+  from starks_b200 import dist as sd
+  from starks_b200.air import witness_limbs
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  F = IntegersModP(P)
+  out = {}
+  unit = lambda k, w: tuple(1 if i == k else 0 for i in range(w))
+  cases = [("fib_w2_2^20", 1 << 20, 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], [0, 1]),
+           ("affine_w8_2^18", 1 << 18, 8, [{unit(j, 8): 1, unit((j + 1) % 8, 8): 1} for j in range(8)],
+            list(range(1, 9)))]
+  for tag, steps, width, sp, inp in cases:
+    res = {"steps": steps, "width": width, "committed_columns": 3 * width, "domain": steps * 8}
+    eng.set_stream(0)
+    wit = witness_limbs(F, inp, steps, width, sp, engine=eng)
+    bnd = [(0, j, inp[j]) for j in range(width)]
+    S = STARK(F, steps, 8, width, sp, engine=eng)
+    for _ in range(2):
+      want = S.mk_proof(wit, bnd)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+      S.mk_proof(wit, bnd)
+    res["one_gpu_ms"] = cx.tmax((time.perf_counter() - t0) / reps * 1e3)
+    prover = sd.ShardedProver(eng, F, steps, 8, width, sp, dev)
+    for _ in range(2):
+      got = prover.mk_proof(wit, bnd)
+    res["equals_one_gpu_proof"] = cx.all_true(got == want if rank == 0 else True)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+      prover.mk_proof(wit, bnd)
+    torch.cuda.synchronize()
+    res["sharded_ms"] = cx.tmax((time.perf_counter() - t0) / reps * 1e3)
+    res["speedup_vs_one_gpu"] = res["one_gpu_ms"] / res["sharded_ms"]
+    res["rank0_phases_ms"] = {k: round(v, 2) for k, v in prover.timings.items() if k.endswith("_ms")}
+    out[tag] = res
+    del prover
+    torch.cuda.empty_cache()
+  line["stark_proof_sharded"] = out
+  line["stark_proof_sharded_ms_fib_2^20_steps_x8"] = out["fib_w2_2^20"]["sharded_ms"]
+  line["stark_proof_sharded_parity_ok"] = all(v["equals_one_gpu_proof"] for v in out.values())
+
+
 # ------------------------------------------------------------------ CPU legs
 
 def cpu_port_baseline(cols_sample, threads):
@@ -570,7 +618,7 @@ def cpu_python_reference(budget_s=150.0):
     merkelize(ev)
     out["merkelize_2^16_s"] = time.perf_counter() - t0
     if time.perf_counter() - t_start < budget_s:
-      from starks.poly_utils import generate_Xi_s
+      from starks.utils import generate_Xi_s
       from starks.air import get_computational_trace
       import starks.stark as us
       steps = 1024
@@ -819,8 +867,11 @@ def main():
   torch.cuda.empty_cache()
   eng.set_stream(0)
   if not args.no_extras:
-    with Watchdog(420, rank, line, "the multi-GPU sections (configs 3 and 4)"):
-      for name, fn in (("lde_merkle_commit", section_config3), ("ntt_2^26", section_config4)):
+    with Watchdog(480, rank, line, "the multi-GPU sections (configs 3, 4 and 5)"):
+      secs = [("lde_merkle_commit", section_config3), ("ntt_2^26", section_config4)]
+      if world > 1:
+        secs.append(("stark_proof_sharded", section_config5_sharded))
+      for name, fn in secs:
         try:
           fn(cx, line)
         except Exception as ex:  # pragma: no cover

@@ -126,6 +126,12 @@ int stk_lde_commit(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64
  * cross-rank barrier each rank runs stk_merkle_commit on its buffer (global node nranks + r). */
 int stk_lde_p2p(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
                 uint64_t cols, const uint32_t g2[8], uint64_t nranks, uint64_t col_base, const uint64_t* peer_ptrs);
+/* Forward transform of `cols` COEFFICIENT rows (n_in coefficients, zero-padded to n) with the same
+ * fused row scatter: the sharded prover's evaluation of its slice of P, D, B (starks/stark.py:247,
+ * 254-256).  cols = 0 is a no-op. */
+int stk_ntt_p2p(stk_ctx* ctx, const uint32_t* d_coeffs, uint64_t n_in, uint64_t in_stride, uint64_t n,
+                uint64_t cols, const uint32_t root[8], uint64_t nranks, uint64_t col_base,
+                const uint64_t* peer_ptrs);
 
 /* ---- Merkle ---------------------------------------------------------------------- */
 /* merkelize_polynomial_evaluations + merkelize (starks/merkle_tree.py:36-56, 94-119) over
@@ -163,6 +169,11 @@ int stk_fri_fold4(stk_ctx* ctx, const uint32_t* d_vals, uint64_t n, const uint32
                   const uint32_t special_x[8], uint32_t* d_out);
 /* get_pseudorandom_indices (starks/utils.py:60-90) as the FRI driver derives them (host BLAKE2s
  * chain over the 32-byte entropy, 4-byte big-endian words).  Host only: ctx may be NULL. */
+/* The same fold for a layer sharded by leaf range (one proof over several GPUs):
+ * d_rows = the four runs {j*n/4 + i0 + t : t < q_run}, j < 4, back to back; d_out receives
+ * column[i0 .. i0 + q_run). */
+int stk_fri_fold4_rows(stk_ctx* ctx, const uint32_t* d_rows, uint64_t n, const uint32_t root[8],
+                       const uint32_t special_x[8], uint64_t q_run, uint64_t i0, uint32_t* d_out);
 int stk_pseudorandom_indices(stk_ctx* ctx, const uint8_t entropy[32], uint64_t modulus, uint64_t count,
                              uint64_t exclude_multiples_of, uint64_t* h_out);
 /* The whole commit phase of SmoothSubgroupFRI.generate_proximity_proof (starks/fri.py:189-266)

@@ -15,8 +15,10 @@ using namespace stk;
 
 namespace {
 
+// i0: index of this launch's first quad in the WHOLE layer (0 unless the layer is sharded by
+// leaf range: a rank then holds the quads i0 .. i0 + q - 1 as four runs of q rows each).
 template <class F>
-__global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ vals, uint64_t q,
+__global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ vals, uint64_t q, uint64_t i0,
                                                         const fe* __restrict__ Winv, uint64_t wstride, fe x_plain, fe iota_tw,
                                                         fe quarter_tw, fe* __restrict__ out, const F f) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ v
   fe m = f.mul_tw(d13, iota_tw);
   fe c0 = f.add(s02, s13), c2 = f.sub(s02, s13);  // 4*b0, 4*b2
   fe c1 = f.sub(d02, m), c3 = f.add(d02, m);      // 4*b1, 4*b3
-  fe t = f.mul_tw(x_plain, fe_load_ro(Winv + i * wstride));  // x * w^-i, plain
+  fe t = f.mul_tw(x_plain, fe_load_ro(Winv + (i0 + i) * wstride));  // x * w^-(i0+i), plain
   fe t_tw = f.to_tw(t);
   fe r = f.add(f.mul_tw(c3, t_tw), c2);
   r = f.add(f.mul_tw(r, t_tw), c1);
@@ -37,20 +39,23 @@ __global__ void __launch_bounds__(256) fri_fold4_kernel(const fe* __restrict__ v
 }  // namespace
 
 // launch only: w a primitive n-th root (checked by the caller), winv = w^-1, x reduced
+// the layer has n points; this launch folds the q_run quads i0 .. i0 + q_run - 1, held at d_vals as
+// four runs of q_run values (q_run = n/4, i0 = 0: the whole layer)
 static int fri_fold4_launch(stk_ctx* c, const uint32_t* d_vals, uint64_t n, const fe& w, const fe& winv, const fe& x,
-                            const fe& quarter_tw, uint32_t* d_out) {
+                            const fe& quarter_tw, uint32_t* d_out, uint64_t q_run = 0, uint64_t i0 = 0) {
   const uint64_t q = n / 4;
+  if (!q_run) q_run = q;
   const fe* Winv;
   uint64_t wstride = 1;
   STK_TRY(stk_get_table_strided(c, winv, n, &Winv, &wstride));
   fe iota_tw = stk_h_to_tw(c, stk_h_pow(c, w, q));
-  unsigned blocks = (unsigned)((q + 255) / 256);
+  unsigned blocks = (unsigned)((q_run + 255) / 256);
   if (c->is_stark)
-    fri_fold4_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, wstride, x, iota_tw, quarter_tw,
-                                                                (fe*)d_out, StarkField());
+    fri_fold4_kernel<StarkField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q_run, i0, Winv, wstride, x, iota_tw,
+                                                                quarter_tw, (fe*)d_out, StarkField());
   else
-    fri_fold4_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q, Winv, wstride, x, iota_tw, quarter_tw,
-                                                               (fe*)d_out, c->mont);
+    fri_fold4_kernel<MontField><<<blocks, 256, 0, c->stream>>>((const fe*)d_vals, q_run, i0, Winv, wstride, x, iota_tw,
+                                                               quarter_tw, (fe*)d_out, c->mont);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }
@@ -67,6 +72,25 @@ extern "C" __attribute__((visibility("default"))) int stk_fri_fold4(stk_ctx* c, 
   fe x = host::reduce(stk_load_fe(special_x), c->p);  // fri.py:229 does not reduce; products do
   fe quarter_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(4), c->p)));
   return fri_fold4_launch(c, d_vals, n, w, stk_h_inv(c, w), x, quarter_tw, d_out);
+}
+
+// stk_fri_fold4 for a layer sharded by leaf range ("shard layer 0 by index range
+// aligned to fold quads"): d_rows holds the four runs {j*q + i0 + t : t < q_run}, j < 4, of the
+// n-point layer back to back (the row order of a rank's local tree under permute4), d_out
+// receives column[i0 .. i0 + q_run).
+extern "C" __attribute__((visibility("default"))) int stk_fri_fold4_rows(stk_ctx* c, const uint32_t* d_rows, uint64_t n,
+                                                                          const uint32_t root[8], const uint32_t special_x[8],
+                                                                          uint64_t q_run, uint64_t i0, uint32_t* d_out) {
+  if (!c || !d_rows || !d_out || !root || !special_x) return STK_EINVAL;
+  if (n == 0 || (n & 3) || q_run == 0 || i0 + q_run > n / 4)
+    return stk_fail(c, STK_EINVAL, "fold-by-4 rows: need n divisible by 4 and i0 + q_run <= n/4");
+  fe w = stk_load_fe(root);
+  fe one = host::reduce(host::from_u64(1), c->p);
+  if (!fe_eq(stk_h_pow(c, w, n), one) || fe_eq(stk_h_pow(c, w, n / 2), one))
+    return stk_fail(c, STK_EINVAL, "root is not a primitive n-th root of unity");
+  fe x = host::reduce(stk_load_fe(special_x), c->p);
+  fe quarter_tw = stk_h_to_tw(c, stk_h_inv(c, host::reduce(host::from_u64(4), c->p)));
+  return fri_fold4_launch(c, d_rows, n, w, stk_h_inv(c, w), x, quarter_tw, d_out, q_run, i0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -77,3 +77,24 @@ STK_API int stk_lde_p2p(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, uin
   peer.ptrs = peer_ptrs;
   return stk_ntt_dev_peer(c, coef, steps, steps, n, cols, G2, peer);
 }
+
+// Forward transform of COEFFICIENT rows (n_in coefficients each, implicitly zero-padded to n)
+// whose final pass scatters every evaluation row to its leaf owner, like stk_lde_p2p: the
+// sharded prover hands each rank a slice of the 3w coefficient vectors P_1..P_w, D_1..D_w,
+// B_1..B_w (starks/stark.py:247, 254-256).  cols may be 0 (a rank without columns still takes
+// part in the barriers and hashes its leaf range).
+STK_API int stk_ntt_p2p(stk_ctx* c, const uint32_t* d_coeffs, uint64_t n_in, uint64_t in_stride, uint64_t n,
+                        uint64_t cols, const uint32_t root[8], uint64_t nranks, uint64_t col_base,
+                        const uint64_t* peer_ptrs) {
+  if (!c || !root || !peer_ptrs || n == 0) return STK_EINVAL;
+  if (cols == 0) return STK_OK;
+  if (!d_coeffs) return STK_EINVAL;
+  if (nranks < 2 || nranks > 8 || (nranks & (nranks - 1))) return stk_fail(c, STK_EINVAL, "2, 4 or 8 ranks");
+  if (n & (n - 1)) return stk_fail(c, STK_EINVAL, "the transform length must be a power of two");
+  stk_peer_leaf peer;
+  peer.g = 0;
+  while ((1ull << peer.g) < nranks) ++peer.g;
+  peer.col0 = (uint32_t)col_base;
+  peer.ptrs = peer_ptrs;
+  return stk_ntt_dev_peer(c, (const fe*)d_coeffs, n_in, in_stride, n, cols, stk_load_fe(root), peer);
+}

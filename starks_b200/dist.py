@@ -223,3 +223,280 @@ class ShardedCommitP2P(object):
     roots = allgather_roots(sub_root, self.group, device=trace.device)
     top = combine_subtree_roots(roots)
     return top[1], top
+
+
+# ---------------------------------------------------------------- one proof over all ranks
+
+def split_columns(ncols: int, world: int):
+  """Contiguous column ranges, sizes differing by at most one: [(c0, c1), ...] per rank (a rank
+  may get none: 6 columns over 8 ranks)."""
+  base, extra = divmod(ncols, world)
+  out, c = [], 0
+  for r in range(world):
+    k = base + (1 if r < extra else 0)
+    out.append((c, c + k))
+    c += k
+  return out
+
+
+def leaf_owner(x: int, n: int, world: int):
+  """Row x of an n-row tree sharded by leaf range -> (owner rank, row index in the owner's local
+  buffer).  Rank d holds rows {j*q + d*q/G + t : j < 4, t < q/G} (q = n/4) in (j, t) order --
+  the rows of a local tree of n/G leaves whose permute4 order is the global one restricted to
+  the subtree under global node G + d (starks/merkle_tree.py:11-33)."""
+  q = n // 4
+  lq = q // world
+  j, i = divmod(x, q)
+  d, t = divmod(i, lq)
+  return d, j * lq + t
+
+
+def extend_branch(local_branch, top_nodes, world: int, d: int):
+  """mk_branch (merkle_tree.py:59-68) of the global tree from the branch inside rank d's
+  subtree: the siblings above the subtree root (global node G + d) come from the replicated
+  top levels."""
+  out = list(local_branch)
+  g = world + d
+  while g > 1:
+    out.append(top_nodes[g ^ 1])
+    g //= 2
+  return out
+
+
+class NcclComm(object):
+  """The sharded prover's exchanges over NCCL + torch symmetric memory (one process per GPU)."""
+
+  def __init__(self, device, group=None):
+    self.group = group if group is not None else dist.group.WORLD
+    self.world, self.rank = _world(group)
+    self.device = device
+    self.hdl = None
+
+  def shared_rows(self, shape):
+    """A buffer every rank can store into: (tensor, [peer pointers])."""
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(shape, dtype=torch.int32, device=self.device)
+    self.hdl = symm_mem.rendezvous(t, self.group)
+    return t, [int(p) for p in self.hdl.buffer_ptrs]
+
+  def rows_barrier(self, engine, channel):
+    self.hdl.barrier(channel=channel)     # device-side, on torch's current stream
+
+  def allgather_roots(self, root):
+    return allgather_roots(root, self.group, device=self.device)
+
+  def allreduce_bytes(self, buf):
+    t = torch.from_numpy(buf).to(self.device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+    return t.cpu().numpy()
+
+  def allgather_column(self, engine, column, col_local):
+    dist.all_gather_into_tensor(column, col_local, group=self.group)
+
+
+class ThreadComm(object):
+  """The same exchanges between G emulated ranks that are THREADS of one process sharing one
+  GPU (each with its own Engine): every exchange is a host-side barrier after a stream
+  synchronisation, so no kernel ever waits on another (tests/test_gpu_dist_emulated.py)."""
+
+  class Shared(object):
+    def __init__(self, world):
+      import threading
+      self.world = world
+      self.bar = threading.Barrier(world, timeout=300)   # a failed rank must not hang the others
+      self.slots = [None] * world
+
+  def __init__(self, shared, rank, device):
+    self.sh, self.rank, self.world, self.device = shared, rank, shared.world, device
+
+  def _exchange(self, value):
+    self.sh.slots[self.rank] = value
+    self.sh.bar.wait()
+    out = list(self.sh.slots)
+    self.sh.bar.wait()
+    return out
+
+  def shared_rows(self, shape):
+    t = torch.empty(shape, dtype=torch.int32, device=self.device)
+    return t, self._exchange(t.data_ptr())
+
+  def rows_barrier(self, engine, channel):
+    engine.sync()
+    self.sh.bar.wait()
+
+  def allgather_roots(self, root):
+    return self._exchange(bytes(root))
+
+  def allreduce_bytes(self, buf):
+    parts = self._exchange(buf)
+    out = parts[0].copy()
+    for x in parts[1:]:
+      out += x
+    return out
+
+  def allgather_column(self, engine, column, col_local):
+    engine.sync()
+    parts = self._exchange(col_local)
+    column.copy_(torch.cat(parts, dim=0))
+    torch.cuda.synchronize()
+    self.sh.bar.wait()
+
+
+class ShardedProver(object):
+  """STARK.mk_proof (starks/stark.py:233-279) for ONE proof over the G ranks of `group`
+  (BASELINE config 5 "on 8 x B200"):
+
+    * every rank derives the 3w coefficient rows P, D, B (STARK.coefficient_rows: transforms of
+      size `steps` and M <= d*steps, replicated -- a few per cent of the work);
+    * the 3w size-N evaluations are split by COLUMN over the ranks and every transform's final
+      pass stores its rows straight into the leaf owner's buffer over NVLink (stk_ntt_p2p): after
+      one barrier every rank holds ALL columns for its leaf range;
+    * leaf hashing, the linear combination l (pointwise), l's tree and FRI layer 0's fold (whole
+      quads {i, i+q, i+2q, i+3q} are local under the permute4 ranges) run on N/G rows per rank;
+      the two commitments are subtrees + an all-gather of 32-byte roots;
+    * opened branches are cut from the local subtrees by the owner of each position and summed
+      into one buffer (every record has exactly one owner);
+    * the folded column (N/4 values) is all-gathered and FRI layers >= 1 run on rank 0
+      (their sizes shrink 4x per layer and every challenge depends on the previous root).
+
+  The proof object (rank 0) is bit-identical to the one-GPU STARK.mk_proof's."""
+
+  def __init__(self, engine, field, steps, extension_factor, width, step_polys, device, group=None, comm=None):
+    from .stark import STARK
+    self.eng = engine
+    self.S = STARK(field, steps, extension_factor, width, step_polys, engine=engine)
+    self.comm = comm if comm is not None else NcclComm(device, group)
+    self.world, self.rank = self.comm.world, self.comm.rank
+    self.device = device
+    N, G, w = self.S.precision, self.world, width
+    assert N % (4 * G) == 0
+    self.n_local = N // G
+    self.rows, self.ptrs = self.comm.shared_rows((3 * w, self.n_local, 8))
+    u8 = dict(dtype=torch.uint8, device=device)
+    i32 = dict(dtype=torch.int32, device=device)
+    self.nodes_m = torch.empty((self.n_local, 32), **u8)
+    self.nodes_l = torch.empty((self.n_local, 32), **u8)
+    self.l_rows = torch.empty((self.n_local, 8), **i32)
+    q = N // 4
+    self.col_local = torch.empty((q // G, 8), **i32)
+    self.column = torch.empty((q, 8), **i32)
+    self.nodes2 = torch.empty((q, 32), **u8)
+    self.timings = {}
+
+  # -- opened branches of a tree sharded by leaf range -------------------------------------
+  def _branches(self, specs):
+    """specs: [(rows tensor, ncols, nodes tensor, top nodes, [global positions]), ...] ->
+    [[branch, ...], ...] on every rank.  Each rank cuts the branches whose leaves it owns; one
+    all-reduce (sum of byte buffers with exactly one non-zero contributor per record) shares them."""
+    N, G = self.S.precision, self.world
+    depth = N.bit_length() - 1
+    recs, total = [], 0
+    for rows, ncols, nodes, top, pos in specs:
+      L = 32 * ncols
+      rec = 2 * L + 32 * (depth - 1)
+      recs.append((L, rec, total))
+      total += rec * len(pos)
+    import numpy as np
+    buf = np.zeros(total, dtype=np.uint8)
+    for (rows, ncols, nodes, top, pos), (L, rec, off) in zip(specs, recs):
+      mine = [(k, leaf_owner(x, N, G)) for k, x in enumerate(pos)]
+      mine = [(k, loc) for k, (d, loc) in mine if d == self.rank]
+      if not mine:
+        continue
+      local = self.eng.merkle_paths(rows.data_ptr(), self.n_local, ncols, self.n_local, nodes.data_ptr(),
+                                    [loc for _, loc in mine])
+      for (k, _), br in zip(mine, local):
+        full = extend_branch(br, top, G, self.rank)
+        b = b"".join(full)
+        assert len(b) == rec
+        buf[off + k * rec:off + (k + 1) * rec] = np.frombuffer(b, dtype=np.uint8)
+    data = self.comm.allreduce_bytes(buf).tobytes()
+    out = []
+    from .engine import _path_struct
+    for (rows, ncols, nodes, top, pos), (L, rec, off) in zip(specs, recs):
+      S = _path_struct(L, depth)
+      out.append([list(x) for x in S.iter_unpack(data[off:off + rec * len(pos)])])
+    return out
+
+  def mk_proof(self, witness, boundary):
+    """Same arguments as STARK.mk_proof; every rank passes the same witness.  Returns the proof
+    on rank 0 (None elsewhere)."""
+    import time
+    from .fri import FRI, DeviceLayer
+    from .limbs import limbs_to_ints
+    from .stark import get_pseudorandom_ks
+    from .utils import get_pseudorandom_indices
+    t0 = time.perf_counter()
+    marks = []
+    mark = lambda name: marks.append((name, time.perf_counter()))
+    S, eng, G, rank = self.S, self.eng, self.world, self.rank
+    p = S.field.p
+    eng.set_field(p)
+    w, steps, ext, N = S.width, S.steps, S.extension_factor, S.precision
+    G2 = int(S.G2)
+    if isinstance(self.comm, NcclComm):
+      _adopt_stream(eng, self.rows)   # order the engine's kernels with torch's collectives
+    tr = S._witness_limbs(witness)
+    d_trace = eng.alloc(w * steps * 32).upload(tr, wait=False)
+    d_coef, cs = S.coefficient_rows(eng, d_trace.ptr, boundary, limbs_to_ints(tr[:, -1, :]))
+    mark("coefficients")
+    c0, c1 = split_columns(3 * w, G)[rank]
+    self.comm.rows_barrier(eng, 0)       # nobody still reads the previous proof's rows
+    eng.ntt_p2p(d_coef.at(c0 * cs * 32), cs, cs, N, c1 - c0, G2, G, c0, self.ptrs)
+    self.comm.rows_barrier(eng, 1)       # all rows have landed
+    sub = eng.merkle_commit(self.rows.data_ptr(), self.n_local, 3 * w, self.n_local, self.nodes_m.data_ptr())
+    top_m = combine_subtree_roots(self.comm.allgather_roots(sub))
+    m_root = top_m[1]
+    mark("m_root")
+    k1, k2, k3, k4 = get_pseudorandom_ks(m_root, 4)
+    l_ks = get_pseudorandom_ks(m_root, w)
+    c = pow(pow(G2, steps, p), N - 1, p)
+    wP, wD, wB = [], [], []
+    for j in range(w):
+      aj = (1 + l_ks[j] * c) % p
+      wD.append(aj)
+      wP.append(aj * ((k1 + k2 * c) % p) % p)
+      wB.append(aj * ((k3 + k4 * c) % p) % p)
+    eng.lincomb(self.rows.data_ptr(), self.n_local, 3 * w, self.n_local, wP + wD + wB, self.l_rows.data_ptr())
+    sub_l = eng.merkle_commit(self.l_rows.data_ptr(), self.n_local, 1, self.n_local, self.nodes_l.data_ptr())
+    top_l = combine_subtree_roots(self.comm.allgather_roots(sub_l))
+    l_root = top_l[1]
+    mark("l_root")
+    positions = get_pseudorandom_indices(l_root, N, 80, exclude_multiples_of=ext)
+    mb, lb = self._branches([
+        (self.rows, 3 * w, self.nodes_m, top_m, [x for pos in positions for x in (pos, (pos + ext) % N)]),
+        (self.l_rows, 1, self.nodes_l, top_l, positions)])
+    branches = []
+    for i in range(len(positions)):
+      branches += [mb[2 * i], mb[2 * i + 1], lb[i]]
+    mark("spot_checks")
+    # FRI layer 0 (fri.py:217-256) on the sharded l, the rest on rank 0
+    maxdeg = steps * S.get_degree()
+    assert maxdeg > 16, "the sharded prover needs at least one FRI fold layer"
+    q = N // 4
+    lq = q // G
+    eng.fri_fold4_rows(self.l_rows.data_ptr(), N, G2, int.from_bytes(l_root, "big"), lq, rank * lq,
+                       self.col_local.data_ptr())
+    self.comm.allgather_column(eng, self.column, self.col_local)
+    root2 = eng.merkle_commit(self.column.data_ptr(), q, 1, q, self.nodes2.data_ptr())
+    ys = get_pseudorandom_indices(root2, q, 40, exclude_multiples_of=ext)
+    (lb0,) = self._branches([(self.l_rows, 1, self.nodes_l, top_l, [y + q * j for y in ys for j in range(4)])])
+    mark("fri_layer0")
+    proof = None
+    if rank == 0:
+      cb = eng.merkle_paths(self.column.data_ptr(), q, 1, q, self.nodes2.data_ptr(), ys)
+      rest = FRI(S.field, engine=eng).prove_from_device(
+          DeviceLayer(eng, self.column.data_ptr(), q, self.nodes2.data_ptr(), root2), pow(G2, 4, p), maxdeg // 4,
+          exclude_multiples_of=ext)
+      fri_proof = [[root2, [[cb[i]] + lb0[4 * i:4 * i + 4] for i in range(len(ys))]]] + rest
+      proof = [m_root, l_root, branches, fri_proof]
+    mark("fri_rest")
+    eng.sync()
+    d_trace.free()
+    d_coef.free()
+    self.timings = {"mk_proof_s": time.perf_counter() - t0}
+    prev = t0
+    for name, t in marks:
+      self.timings[name + "_ms"] = (t - prev) * 1e3
+      prev = t
+    return proof

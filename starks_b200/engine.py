@@ -212,6 +212,24 @@ class Engine:
     self._check(self.lib.stk_lde_p2p(self.ctx, d_trace, steps, trace_stride, ext, cols,
                                      _u32(int_to_limbs(int(g2) % self.p)), nranks, col_base, arr))
 
+  def ntt_p2p(self, d_coeffs, n_in, in_stride, n, cols, root, nranks, col_base, peer_ptrs):
+    """Forward transform of coefficient rows whose final pass scatters rows to their leaf owners
+    (stk_ntt_p2p); cols may be 0."""
+    arr = (ctypes.c_uint64 * nranks)(*[int(p) for p in peer_ptrs])
+    self._check(self.lib.stk_ntt_p2p(self.ctx, d_coeffs, n_in, in_stride, n, cols,
+                                     _u32(int_to_limbs(int(root) % self.p)), nranks, col_base, arr))
+
+  def lincomb(self, d_cols, n, ncols, col_stride, weights, d_out):
+    """out[i] = sum_c weights[c] * cols[c][i] (stk_lincomb); weights: list of ints."""
+    from .limbs import ints_to_limbs
+    wl = ints_to_limbs([int(x) % self.p for x in weights])
+    self._check(self.lib.stk_lincomb(self.ctx, d_cols, n, ncols, col_stride, wl.ctypes.data, d_out))
+
+  def fri_fold4_rows(self, d_rows, n, root, special_x, q_run, i0, d_out):
+    """Fold of the quads i0 .. i0+q_run-1 of an n-point layer held as four runs (stk_fri_fold4_rows)."""
+    self._check(self.lib.stk_fri_fold4_rows(self.ctx, d_rows, n, _u32(int_to_limbs(int(root) % self.p)),
+                                            _u32(int_to_limbs(int(special_x))), q_run, i0, d_out))
+
   def lde_commit(self, d_trace, steps, trace_stride, ext, cols, g2, d_evals, eval_stride, d_nodes):
     root = (ctypes.c_uint8 * 32)()
     self._check(self.lib.stk_lde_commit(self.ctx, d_trace, steps, trace_stride, ext, cols,

@@ -150,10 +150,8 @@ if hasattr(sd, "ShardedProver"):
            (1 << 11, 8, None, None)]
   if full:
     cases.append((1 << 20, 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], [0, 1]))
-    cases.append((1 << 16, 16, None, None))
+    cases.append((1 << 15, 12, None, None))   # 36 columns: uneven split over 8 ranks (width <= 12)
   for steps, width, sp, inp in cases:
-    if width % world and (3 * width) % world:
-      continue
     if sp is None:  # a wide affine AIR: x_j' = x_j + x_(j+1 mod w)
       unit = lambda k: tuple(1 if i == k else 0 for i in range(width))
       sp = [{unit(j): 1, unit((j + 1) % width): 1} for j in range(width)]

@@ -177,3 +177,33 @@ def test_pack_rows_single_process():
   import hashlib
   assert top[2] == hashlib.blake2s(roots[0] + roots[1]).digest() and set(top) == set(range(1, 8))
   assert output_owner(5, 4) == (2, 1) and output_owner(6, 4) == (1, 1) and output_owner(7, 1) == (0, 7)
+
+
+def test_sharded_tree_branches_equal_global_branches(oracle):
+  """Index logic of the sharded prover (dist.leaf_owner / extend_branch / split_columns): a branch
+  cut from the owner's subtree and extended through the replicated top levels is exactly
+  mk_branch of the one big tree (starks/merkle_tree.py:59-68)."""
+  from starks_b200.dist import leaf_owner, extend_branch, split_columns, combine_subtree_roots
+  n = 64
+  leaves = [oracle.blake(bytes([i])) for i in range(n)]
+  tree = oracle.merkelize(leaves)
+  for world in (2, 4, 8):
+    q, lq = n // 4, n // 4 // world
+    local_rows = [[leaves[j * q + d * lq + t] for j in range(4) for t in range(lq)] for d in range(world)]
+    local_trees = [oracle.merkelize(r) for r in local_rows]
+    top = combine_subtree_roots([t[1] for t in local_trees])
+    assert top[1] == tree[1]
+    for i in range(1, 2 * world):
+      assert top[i] == tree[i]
+    seen = set()
+    for x in range(n):
+      d, loc = leaf_owner(x, n, world)
+      assert local_rows[d][loc] == leaves[x]
+      seen.add((d, loc))
+      br = extend_branch(oracle.mk_branch(local_trees[d], loc), top, world, d)
+      assert br == oracle.mk_branch(tree, x)
+      assert oracle.verify_branch(tree[1], x, br) == leaves[x]
+    assert len(seen) == n
+  assert split_columns(6, 8) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 6), (6, 6)]
+  assert split_columns(6, 4) == [(0, 2), (2, 4), (4, 5), (5, 6)]
+  assert split_columns(48, 8)[3] == (18, 24)

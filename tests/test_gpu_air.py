@@ -104,3 +104,78 @@ def test_pointwise_quotients_equal_transform_route(eng, oracle, monkeypatch):
     if steps <= 256:
       want = oracle.StarkOracle(steps, ext, width, sp).mk_proof(oracle.computational_trace(P, inp, steps, sp), boundary)
       assert got["1"][0] == want
+
+
+AFFINE = [
+    ("fibonacci", [0, 1], [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]),
+    ("affine+const", [2, 5], [{(1, 0): 1, (0, 0): 7}, {(1, 0): 1, (0, 1): 3, (0, 0): P - 2}]),
+    ("3-wide rotate", [1, 2, 3], [{(0, 1, 0): 1}, {(0, 0, 1): 1}, {(1, 0, 0): 5, (0, 1, 0): 1}]),
+]
+
+
+@pytest.mark.parametrize("name,inp,sp", AFFINE, ids=[c[0] for c in AFFINE])
+@pytest.mark.parametrize("steps", [1, 2, 63, 4096, 5000, 1 << 16])
+def test_device_trace_affine_chunked(eng, oracle, name, inp, sp, steps):
+  """stk_trace_generate_dev on AIRs of degree <= 1: from 4096 steps on, one trace runs as parallel
+  chunks whose start states are powers of the companion matrix -- equal to the sequential
+  recurrence (starks/air.py:31-52) element for element, ragged last chunk included."""
+  from starks_b200.air import witness_device, witness_limbs
+  from starks_b200.modp import IntegersModP
+  F = IntegersModP(P)
+  width = len(inp)
+  d_w = witness_device(F, inp, steps, width, sp, engine=eng)
+  got = d_w.download((width, steps, 8))
+  d_w.free()
+  want = witness_limbs(F, inp, steps, width, sp, engine=eng)
+  assert (got == want).all()
+  if steps <= 4096:
+    ref = oracle.computational_trace(P, inp, steps, sp)
+    for j in range(width):
+      assert oracle.from_limbs(got[j]) == ref[j]
+
+
+def test_device_traces_batch_and_nonlinear(eng, oracle):
+  """Many independent traces of a NON-linear AIR, one thread each; and a single non-linear trace
+  through the host recurrence with the upload overlapped (stk_trace_generate_upload)."""
+  from starks_b200.air import witness_device, witness_limbs
+  from starks_b200.modp import IntegersModP
+  F = IntegersModP(P)
+  sp = [{(0, 1): 1}, {(1, 0): 1, (0, 3): 1, (0, 0): 42}]
+  steps, nt = 300, 37
+  inputs = [[i + 1, 2 * i + 5] for i in range(nt)]
+  d_w = witness_device(F, inputs, steps, 2, sp, engine=eng, ntraces=nt)
+  got = d_w.download((nt, 2, steps, 8))
+  d_w.free()
+  for t in (0, 1, 17, nt - 1):
+    ref = oracle.computational_trace(P, inputs[t], steps, sp)
+    for j in range(2):
+      assert oracle.from_limbs(got[t, j]) == ref[j], (t, j)
+  steps = (1 << 16) + 77            # three upload blocks, the last one ragged
+  d_w = witness_device(F, [2, 3], steps, 2, sp, engine=eng)
+  eng.sync()
+  got = d_w.download((2, steps, 8))
+  d_w.free()
+  assert (got == witness_limbs(F, [2, 3], steps, 2, sp, engine=eng)).all()
+
+
+def test_prover_takes_a_device_witness_and_rejects_noncanonical_limbs(eng, oracle):
+  from starks_b200.air import witness_device, witness_limbs
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  F = IntegersModP(P)
+  sp = [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}]
+  steps = 1 << 12
+  bnd = [(0, 0, 0), (0, 1, 1)]
+  S = STARK(F, steps, 8, 2, sp, engine=eng)
+  host = witness_limbs(F, [0, 1], steps, 2, sp, engine=eng)
+  d_w = witness_device(F, [0, 1], steps, 2, sp, engine=eng)
+  proof = S.mk_proof(d_w, bnd)
+  assert proof == S.mk_proof(host, bnd)
+  assert S.verify_proof(proof, d_w, bnd)
+  d_w.free()
+  # limbs >= p are not field elements: the array path must refuse them (the list path reduces)
+  bad = host.copy()
+  bad[1, 5] = np.array([0xFFFFFFFF] * 8, dtype=np.uint32)
+  with pytest.raises(ValueError):
+    S.mk_proof(bad, bnd)
+  assert eng.count_noncanonical(eng.alloc(bad.nbytes).upload(bad).ptr, 2 * steps) == 1

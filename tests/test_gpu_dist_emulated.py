@@ -151,3 +151,60 @@ def test_lde_with_fused_leaf_exchange_emulated(eng, world, logsteps, ncols):
       gi = (world + r) * (1 << dd) + (i - (1 << dd))
       assert (loc[i] == full[gi]).all(), (r, i)
   assert combine_subtree_roots(roots)[1] == root
+
+
+@pytest.mark.parametrize("world,logsteps,air", [(2, 9, "fib"), (4, 10, "fib"), (8, 11, "fib"), (4, 9, "quad"),
+                                                (8, 9, "w4")])
+def test_sharded_prover_emulated(oracle, world, logsteps, air):
+  """dist.ShardedProver -- ONE proof over G ranks (BASELINE config 5 "on 8 x B200") -- with the
+  ranks emulated as G threads on cuda:0 (dist.ThreadComm: every exchange is a host-side barrier
+  after a stream synchronisation): column-sharded evaluation of P, D, B with the row scatter of
+  stk_ntt_p2p (uneven splits: 6 columns over 8 ranks), subtrees + replicated top levels, the
+  linear combination and FRI layer 0 on leaf ranges, branches cut by their owners.  The proof
+  must be the one-GPU proof, object for object; the NCCL / symmetric-memory plumbing of the same
+  class runs in tests/test_gpu_multi.py."""
+  import threading
+  import torch
+  from starks_b200 import Engine
+  from starks_b200.dist import ShardedProver, ThreadComm
+  from starks_b200.modp import IntegersModP
+  from starks_b200.stark import STARK
+  steps = 1 << logsteps
+  F = IntegersModP(P)
+  if air == "fib":
+    width, sp, inp = 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], [0, 1]
+  elif air == "quad":
+    width, sp, inp = 2, [{(0, 1): 1}, {(1, 0): 1, (0, 2): 2}], [2, 5]
+  else:
+    width, inp = 4, [1, 2, 3, 4]
+    sp = [{(0, 1, 0, 0): 1}, {(0, 0, 1, 1): 1}, {(2, 1, 0, 0): 1, (0, 0, 0, 1): 1}, {(1, 0, 0, 0): 1, (0, 1, 1, 0): 3}]
+  wit = oracle.computational_trace(P, inp, steps, sp)
+  bnd = [(0, j, inp[j]) for j in range(width)]
+  e0 = Engine(0)
+  want = STARK(F, steps, 8, width, sp, engine=e0).mk_proof(wit, bnd)
+  e0.close()
+  dev = torch.device("cuda", 0)
+  shared = ThreadComm.Shared(world)
+  results, errors = [None] * world, []
+
+  def run(r):
+    try:
+      torch.cuda.set_device(0)
+      eng = Engine(0)
+      prover = ShardedProver(eng, F, steps, 8, width, sp, dev, comm=ThreadComm(shared, r, dev))
+      first = prover.mk_proof(wit, bnd)
+      results[r] = prover.mk_proof(wit, bnd)     # second proof: the row buffers are reused
+      assert first == results[r]
+      eng.close()
+    except BaseException as ex:  # noqa: BLE001
+      errors.append((r, repr(ex)))
+      shared.bar.abort()
+
+  threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join(timeout=600)
+  assert not errors, errors
+  assert results[0] == want, "sharded proof differs from the one-GPU proof"
+  assert all(x is None for x in results[1:])

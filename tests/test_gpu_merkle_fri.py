@@ -261,4 +261,20 @@ def test_batched_branch_verification(eng, oracle):
         eng.verify_branches(root, idx, bad)
     with pytest.raises(AssertionError):       # right branches, wrong positions
       eng.verify_branches(root, idx[1:] + idx[:1], brs)
+    # Same committed bytes, element boundaries shifted: the packed record still hashes to the root,
+    # but b[0] is no longer the committed leaf -- must be refused (the reference hashes exactly the
+    # proof[0] it returns, merkle_tree.py:71-86).
+    if len(idx) > 1:
+      for cut in (1, 31, 32):
+        bad = [list(b) for b in brs]
+        b = bad[1]
+        bad[1] = [b[0][:-cut], b[0][-cut:] + b[1]] + b[2:]
+        with pytest.raises(AssertionError):
+          eng.verify_branches(root, idx, bad)
+      bad = [list(b) for b in brs]
+      if len(bad[1]) > 3:
+        b = bad[1]
+        bad[1] = b[:2] + [b[2] + b[3][:1], b[3][1:]] + b[4:]
+        with pytest.raises(AssertionError):
+          eng.verify_branches(root, idx, bad)
     d.free(); nodes.free()

@@ -82,7 +82,7 @@ def _upstream_case(starks, steps):
   from starks.modp import IntegersModP
   from starks.polynomial import polynomials_over  # noqa: F401
   from starks.multivariate_polynomial import multivariates_over  # noqa: F401
-  from starks.poly_utils import generate_Xi_s
+  from starks.utils import generate_Xi_s
   from starks.air import get_computational_trace
   F = IntegersModP(P)
   Xs = generate_Xi_s(F, 2)
@@ -133,7 +133,7 @@ def test_upstream_verifier_accepts_gpu_proof_2p12(upstream):
   eng.close()
   with pyref.quiet():
     from starks.modp import IntegersModP
-    from starks.poly_utils import generate_Xi_s
+    from starks.utils import generate_Xi_s
     import starks.stark as us
     import starks.merkle_tree as umt
     import hashlib
