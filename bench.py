@@ -330,6 +330,15 @@ def section_config3(cx, line, reps=4):
     t0 = time.perf_counter()
     for _ in range(reps):
       e2e()
+    out["e2e_copy_then_commit_ms"] = (time.perf_counter() - t0) / reps * 1e3
+
+    def e2e_api():   # the host-trace entry point: upload pipelined with the transforms
+      return eng.lde_commit_host(h_tr.array, ext, g2, d_ev1.data_ptr(), n, d_nodes.data_ptr())
+    assert e2e_api() == want_root
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+      e2e_api()
     out["e2e_ms"] = (time.perf_counter() - t0) / reps * 1e3
     del d_ev1
   else:

@@ -119,6 +119,13 @@ int stk_lde_commit(stk_ctx* ctx, const uint32_t* d_trace, uint64_t steps, uint64
                    uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride, uint8_t* d_nodes,
                    uint8_t* h_root);
 
+/* stk_lde_commit with the trace in HOST memory (pinned, stk_host_alloc): column groups are uploaded
+ * on a copy stream while the previous group is transformed, so only the first group's copy is
+ * exposed.  The end-to-end form of "LDE + Merkle commit": trace on the host -> root on the host. */
+int stk_lde_commit_host(stk_ctx* ctx, const uint32_t* h_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                        uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride,
+                        uint8_t* d_nodes, uint8_t* h_root);
+
 /* stk_lde for a column shard with the commit's exchange fused in: the final pass of the forward
  * transform stores every evaluation row straight into the rank that owns the row's leaf range
  * (peer_ptrs[r] = rank r's (cols_total x N/nranks) row buffer mapped into this process; rows

@@ -54,6 +54,7 @@ SIGNATURES = {
     "stk_lde_p2p": (cint, [vp, vp, u64, u64, u64, u64, u32p, u64, u64, u64p]),
     "stk_ntt_p2p": (cint, [vp, vp, u64, u64, u64, u64, u32p, u64, u64, u64p]),
     "stk_fri_fold4_rows": (cint, [vp, vp, u64, u32p, u32p, u64, u64, vp]),
+    "stk_lde_commit_host": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, vp]),
     "stk_lde_commit": (cint, [vp, vp, u64, u64, u64, u64, u32p, vp, u64, vp, vp]),
     "stk_merkle_commit": (cint, [vp, vp, u64, u64, u64, vp, vp]),
     "stk_merkle_commit_raw": (cint, [vp, vp, u64, u64, vp, vp]),

@@ -4,6 +4,7 @@
 // forward NTT over <G2>, G1 = G2^ext) and merkelize_polynomial_evaluations (:257).  There is
 // no coset shift in the reference: the evaluation domain is the subgroup <G2> itself, so
 // evals[i*ext] == trace[i].
+#include <algorithm>
 #include "ctx.h"
 
 using namespace stk;
@@ -97,4 +98,44 @@ STK_API int stk_ntt_p2p(stk_ctx* c, const uint32_t* d_coeffs, uint64_t n_in, uin
   peer.col0 = (uint32_t)col_base;
   peer.ptrs = peer_ptrs;
   return stk_ntt_dev_peer(c, (const fe*)d_coeffs, n_in, in_stride, n, cols, stk_load_fe(root), peer);
+}
+
+// stk_lde_commit with the trace in HOST memory (pinned: stk_host_alloc) -- the end-to-end form of
+// BASELINE's "LDE + Merkle-commit" metric (trace on the host -> root on the host).  Columns are
+// independent until the leaves are hashed, so the upload is pipelined with the transforms: column
+// groups stream through two staging slots on a copy stream while the previous group's inverse
+// and forward transforms run on the compute stream; only the first group's copy is exposed.
+STK_API int stk_lde_commit_host(stk_ctx* c, const uint32_t* h_trace, uint64_t steps, uint64_t trace_stride, uint64_t ext,
+                                uint64_t cols, const uint32_t g2[8], uint32_t* d_evals, uint64_t eval_stride,
+                                uint8_t* d_nodes, uint8_t* h_root) {
+  if (!c || !h_trace || !d_evals || !d_nodes || !g2 || steps == 0 || ext == 0 || cols == 0 || trace_stride < steps)
+    return STK_EINVAL;
+  const uint64_t n = steps * ext;
+  const uint64_t col_bytes = steps * sizeof(fe);
+  uint64_t chunk = std::max<uint64_t>(1, ((uint64_t)32 << 20) / col_bytes);
+  chunk = std::min(chunk, cols);
+  void* st;
+  STK_TRY(stk_scratch(c, 11, 2 * chunk * col_bytes, &st));
+  fe* slot[2] = {(fe*)st, (fe*)st + chunk * steps};
+  cudaStream_t cp = c->copy_streams[0];
+  // the staging slots may still be read by transforms of an earlier call on the compute stream
+  STK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  STK_CUDA(c, cudaStreamWaitEvent(cp, c->ev[0], 0));
+  int k = 0;
+  for (uint64_t b0 = 0; b0 < cols; b0 += chunk, k ^= 1) {
+    const uint64_t nb = std::min(chunk, cols - b0);
+    cudaEvent_t up = c->ev[1 + k], done = c->ev[3 + k];
+    if (b0 >= 2 * chunk) STK_CUDA(c, cudaStreamWaitEvent(cp, done, 0));   // slot k's previous group is transformed
+    if (trace_stride == steps)
+      STK_CUDA(c, cudaMemcpyAsync(slot[k], h_trace + b0 * trace_stride * 8, nb * col_bytes, cudaMemcpyHostToDevice, cp));
+    else
+      STK_CUDA(c, cudaMemcpy2DAsync(slot[k], col_bytes, h_trace + b0 * trace_stride * 8, trace_stride * sizeof(fe),
+                                    col_bytes, nb, cudaMemcpyHostToDevice, cp));
+    STK_CUDA(c, cudaEventRecord(up, cp));
+    STK_CUDA(c, cudaStreamWaitEvent(c->stream, up, 0));
+    STK_TRY(stk_lde(c, (const uint32_t*)slot[k], steps, steps, ext, nb, g2, nullptr, 0,
+                    d_evals + b0 * eval_stride * 8, eval_stride));
+    STK_CUDA(c, cudaEventRecord(done, c->stream));
+  }
+  return stk_merkle_commit(c, d_evals, n, cols, eval_stride, d_nodes, h_root);
 }

@@ -71,7 +71,7 @@ extern "C" __attribute__((visibility("default"))) void stk_destroy(stk_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& t : c->tables) cudaFree(t.d);
   stk_stark_release(c);
-  for (int i = 0; i < 10; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  for (int i = 0; i < stk_ctx::kScratchSlots; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
   for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 3; ++i) if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);

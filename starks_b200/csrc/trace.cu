@@ -145,7 +145,7 @@ STK_API int stk_count_noncanonical(stk_ctx* c, const uint32_t* d_vals, uint64_t 
   *h_bad = 0;
   if (!n) return STK_OK;
   void* t;
-  STK_TRY(stk_scratch(c, 5, 64, &t));   // its own slot: the counter outlives this call when sync = 0
+  STK_TRY(stk_scratch(c, 10, 64, &t));  // its own slot: the counter outlives this call when sync = 0
   STK_CUDA(c, cudaMemsetAsync(t, 0, 4, c->stream));
   noncanonical_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const fe*)d_vals, n, c->p, (uint32_t*)t);
   STK_CUDA(c, cudaGetLastError());

@@ -236,6 +236,15 @@ class Engine:
                                         _u32(int_to_limbs(int(g2) % self.p)), d_evals, eval_stride, d_nodes, root))
     return bytes(root)
 
+  def lde_commit_host(self, h_trace, ext, g2, d_evals, eval_stride, d_nodes):
+    """stk_lde_commit_host: h_trace is a (cols, steps, 8) uint32 HOST array (pinned for overlap)."""
+    cols, steps, _ = h_trace.shape
+    assert h_trace.dtype == np.uint32 and h_trace.flags["C_CONTIGUOUS"]
+    root = (ctypes.c_uint8 * 32)()
+    self._check(self.lib.stk_lde_commit_host(self.ctx, h_trace.ctypes.data, steps, steps, ext, cols,
+                                             _u32(int_to_limbs(int(g2) % self.p)), d_evals, eval_stride, d_nodes, root))
+    return bytes(root)
+
   def merkle_commit(self, d_cols, n, ncols, col_stride, d_nodes, want_root=True):
     root = (ctypes.c_uint8 * 32)()
     self._check(self.lib.stk_merkle_commit(self.ctx, d_cols, n, ncols, col_stride, d_nodes,

@@ -278,3 +278,28 @@ def test_batched_branch_verification(eng, oracle):
         with pytest.raises(AssertionError):
           eng.verify_branches(root, idx, bad)
     d.free(); nodes.free()
+
+
+def test_lde_commit_from_host_trace(eng, oracle):
+  """stk_lde_commit_host (upload pipelined with the transforms) == stk_lde_commit on the same
+  trace: root, nodes and evaluations; ragged last column group, strided host rows."""
+  rng = np.random.default_rng(77)
+  for steps, ncols in ((1 << 10, 3), (1 << 14, 70), (1 << 17, 9)):
+    ext = 8
+    n = steps * ext
+    g2 = pow(7, (P - 1) // n, P)
+    pin = eng.pinned((ncols, steps, 8))
+    pin.array[...] = rand_cols(rng, ncols, steps)
+    d_tr = eng.alloc(pin.array.nbytes).upload(pin.array)
+    ev_a, ev_b = eng.alloc(ncols * n * 32), eng.alloc(ncols * n * 32)
+    no_a, no_b = eng.alloc(32 * n), eng.alloc(32 * n)
+    want = eng.lde_commit(d_tr.ptr, steps, steps, ext, ncols, g2, ev_a.ptr, n, no_a.ptr)
+    for rep in range(2):
+      got = eng.lde_commit_host(pin.array, ext, g2, ev_b.ptr, n, no_b.ptr)
+      assert got == want
+    assert (no_a.download((n, 32), np.uint8)[1:] == no_b.download((n, 32), np.uint8)[1:]).all()
+    for c in (0, ncols - 1):
+      assert (ev_a.download((n, 8), byte_offset=c * n * 32) == ev_b.download((n, 8), byte_offset=c * n * 32)).all()
+    for b in (d_tr, ev_a, ev_b, no_a, no_b):
+      b.free()
+    pin.free()
