@@ -55,9 +55,13 @@ LOGN = 20
 N = 1 << LOGN
 INT_OPS_PER_BUTTERFLY = 264       # SURVEY.md 8(d), frozen
 BYTES_PER_ELEM = 64               # read once + write once
-# measured once per change with ncu (profiles/r01b_ncu_ntt_pass_summary.txt): the two passes of
-# one step move 4.45 GB and 4.25 GB; each pass reads and writes the whole 2 GiB batch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 4.35e9
+# measured once per change with ncu (profiles/r02_ncu_ntt_pass_summary.txt): the two passes of
+# one step move 4.44 GB and 4.24 GB; each pass reads and writes the whole 2 GiB batch
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 4.34e9
+NCU_SOURCE = "profiles/r02_ncu_ntt_pass_summary.txt"
+# per butterfly in the pass kernel's SASS: 64 (product) + 8 (fold by 351) half-rate wide multiply-adds
+WIDE_MACS_PER_BUTTERFLY = 72
+NCU_FMAHEAVY_ACTIVE_PCT = (72.3, 70.2)   # first pass, final pass
 WORKLOAD = "forward NTT, %d columns x 2^20 per GPU, p = 2^256-351*2^32+1 (BASELINE configs[1] at its headline size)"
 
 
@@ -543,11 +547,11 @@ def section_config5_sharded(cx, line, reps=3):
   AIR (24 committed columns over a 2^21-point domain), where the column split has something to divide."""
   torch, eng, world, rank, dev = cx.torch, cx.eng, cx.world, cx.rank, cx.dev
   from starks_b200 import dist as sd
-  from starks_b200.air import witness_limbs
+  from starks_b200.air import witness_device
   from starks_b200.modp import IntegersModP
   from starks_b200.stark import STARK
   F = IntegersModP(P)
-  out = {}
+  out = {"witness": "device-resident on every rank (air.witness_device), for the one-GPU and the sharded prover alike"}
   unit = lambda k, w: tuple(1 if i == k else 0 for i in range(w))
   cases = [("fib_w2_2^20", 1 << 20, 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], [0, 1]),
            ("affine_w8_2^18", 1 << 18, 8, [{unit(j, 8): 1, unit((j + 1) % 8, 8): 1} for j in range(8)],
@@ -555,7 +559,8 @@ def section_config5_sharded(cx, line, reps=3):
   for tag, steps, width, sp, inp in cases:
     res = {"steps": steps, "width": width, "committed_columns": 3 * width, "domain": steps * 8}
     eng.set_stream(0)
-    wit = witness_limbs(F, inp, steps, width, sp, engine=eng)
+    wit = witness_device(F, inp, steps, width, sp, engine=eng)   # device-resident witness on every rank
+    eng.sync()
     bnd = [(0, j, inp[j]) for j in range(width)]
     S = STARK(F, steps, 8, width, sp, engine=eng)
     for _ in range(2):
@@ -579,10 +584,11 @@ def section_config5_sharded(cx, line, reps=3):
     res["rank0_phases_ms"] = {k: round(v, 2) for k, v in prover.timings.items() if k.endswith("_ms")}
     out[tag] = res
     del prover
+    wit.free()
     torch.cuda.empty_cache()
   line["stark_proof_sharded"] = out
   line["stark_proof_sharded_ms_fib_2^20_steps_x8"] = out["fib_w2_2^20"]["sharded_ms"]
-  line["stark_proof_sharded_parity_ok"] = all(v["equals_one_gpu_proof"] for v in out.values())
+  line["stark_proof_sharded_parity_ok"] = all(v["equals_one_gpu_proof"] for v in out.values() if isinstance(v, dict))
 
 
 # ------------------------------------------------------------------ CPU legs
@@ -817,8 +823,8 @@ def main():
     mb = {}
     try:
       eng.set_stream(0)
-      for which, name in ((7, "imad_iadd3_mixed_gops"), (0, "imad_gops"), (1, "imad_wide_gops"), (6, "butterfly_gops"),
-                          (5, "field_mul_gops")):
+      for which, name in ((7, "imad_iadd3_mixed_gops"), (0, "imad_gops"), (10, "imad_wide_carry_rows_gops"),
+                          (6, "butterfly_gops"), (5, "field_mul_gops")):
         best = 0.0
         for _ in range(2):
           mms, ops = eng.microbench(which, 4000 if which not in (5, 6) else 1000)
@@ -845,7 +851,7 @@ def main():
         "roofline": {"bound": "int32", "achieved": int_achieved / 1e3, "peak": (int_peak or 0) / 1e3, "unit": "Tops/s",
                      "frac": (int_achieved / int_peak) if int_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_ncu_ntt_pass_summary.txt",
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, " + NCU_SOURCE,
                      "kernel": "ntt_pass_kernel<StarkField>", "launches_per_step": launches_per_step,
                      "alg_int32_ops_per_step": int_ops, "alg_int32_ops_per_launch": int_ops / launches_per_step,
                      "peak_source": "K0 microbenchmark of this run (IMAD + IADD3 on independent chains, dual issue); "
@@ -856,6 +862,16 @@ def main():
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                              "alg_bytes_per_launch": alg_bytes / launches_per_step, "alg_bytes_per_step": alg_bytes,
                              "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+                     "binding_pipe": {
+                         "name": "fmaheavy: IMAD.WIDE.U32(.X), the half-rate 32x32+64 multiply-add (4 clk per warp instruction)",
+                         "wide_macs_per_butterfly": WIDE_MACS_PER_BUTTERFLY,
+                         "achieved_wide_macs_tops": WIDE_MACS_PER_BUTTERFLY * butterflies / (ms_step * 1e-3) / 1e12,
+                         "peak_wide_macs_tops": (mb.get("imad_wide_carry_rows_gops") or 0) / 1e3,
+                         "frac": (WIDE_MACS_PER_BUTTERFLY * butterflies / (ms_step * 1e-3) / 1e9 / mb["imad_wide_carry_rows_gops"])
+                         if mb.get("imad_wide_carry_rows_gops") else None,
+                         "ncu_pipe_fmaheavy_cycles_active_pct": list(NCU_FMAHEAVY_ACTIVE_PCT),
+                         "note": "ncu (" + NCU_SOURCE + "): the pipe is 72 % / 70 % active in the two passes -- the multiply-adds plus the "
+                                 "moves ptxas places on the same pipe; ALU pipe 46 %, issue slots 49 %, DRAM 12 %"},
                      "microbench": mb,
                      "note": "256-bit modular butterflies: ~41 int32 op per byte against a machine balance of ~4.7, so "
                              "the integer pipes bind and HBM is ~12 % busy (ncu)"},

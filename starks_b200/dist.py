@@ -15,6 +15,7 @@ so they are exercised on CPU tensors with gloo (tests/test_dist_gloo.py); the co
 are the engine's device kernels."""
 from hashlib import blake2s
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -396,7 +397,6 @@ class ShardedProver(object):
       rec = 2 * L + 32 * (depth - 1)
       recs.append((L, rec, total))
       total += rec * len(pos)
-    import numpy as np
     buf = np.zeros(total, dtype=np.uint8)
     for (rows, ncols, nodes, top, pos), (L, rec, off) in zip(specs, recs):
       mine = [(k, leaf_owner(x, N, G)) for k, x in enumerate(pos)]
@@ -437,8 +437,14 @@ class ShardedProver(object):
     if isinstance(self.comm, NcclComm):
       _adopt_stream(eng, self.rows)   # order the engine's kernels with torch's collectives
     tr = S._witness_limbs(witness)
-    d_trace = eng.alloc(w * steps * 32).upload(tr, wait=False)
-    d_coef, cs = S.coefficient_rows(eng, d_trace.ptr, boundary, limbs_to_ints(tr[:, -1, :]))
+    on_device = not isinstance(tr, np.ndarray)      # a DevBuf (air.witness_device): nothing to upload
+    if on_device:
+      d_trace = tr
+      last_rows = np.stack([d_trace.download((1, 8), byte_offset=(j * steps + steps - 1) * 32)[0] for j in range(w)])
+    else:
+      d_trace = eng.alloc(w * steps * 32).upload(tr, wait=False)
+      last_rows = tr[:, -1, :]
+    d_coef, cs = S.coefficient_rows(eng, d_trace.ptr, boundary, limbs_to_ints(last_rows))
     mark("coefficients")
     c0, c1 = split_columns(3 * w, G)[rank]
     self.comm.rows_barrier(eng, 0)       # nobody still reads the previous proof's rows
@@ -492,7 +498,8 @@ class ShardedProver(object):
       proof = [m_root, l_root, branches, fri_proof]
     mark("fri_rest")
     eng.sync()
-    d_trace.free()
+    if not on_device:
+      d_trace.free()
     d_coef.free()
     self.timings = {"mk_proof_s": time.perf_counter() - t0}
     prev = t0

@@ -150,7 +150,7 @@ if hasattr(sd, "ShardedProver"):
            (1 << 11, 8, None, None)]
   if full:
     cases.append((1 << 20, 2, [{(0, 1): 1}, {(1, 0): 1, (0, 1): 1}], [0, 1]))
-    cases.append((1 << 15, 12, None, None))   # 36 columns: uneven split over 8 ranks (width <= 12)
+    cases.append((1 << 15, 9, None, None))   # 27 columns: uneven split (get_pseudorandom_ks serves widths below 10, stark.py:118-126)
   for steps, width, sp, inp in cases:
     if sp is None:  # a wide affine AIR: x_j' = x_j + x_(j+1 mod w)
       unit = lambda k: tuple(1 if i == k else 0 for i in range(width))
