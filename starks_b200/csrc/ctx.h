@@ -113,6 +113,9 @@ int stk_merkle_paths_dev(stk_ctx* c, const stk::fe* d_cols, uint64_t n, uint64_t
 int stk_merkle_finish(stk_ctx* c, uint8_t* d_nodes, uint64_t np, uint8_t* h_root);
 int stk_ntt_dev(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, stk::fe* d_out,
                 uint64_t out_stride, uint64_t n, uint64_t batch, const stk::fe& root, int inverse, int scale);
+int stk_ntt_dev_r0(stk_ctx* c, const stk::fe* d_in, uint64_t n_in, uint64_t in_stride, stk::fe* d_out,
+                   uint64_t out_stride, uint64_t n, uint64_t batch, const stk::fe& root, const stk::fe* r0,
+                   uint64_t r0_stride);
 // field-generic host helpers
 stk::fe stk_h_mul(stk_ctx* c, const stk::fe& a, const stk::fe& b);
 stk::fe stk_h_pow(stk_ctx* c, const stk::fe& a, uint64_t e);

@@ -30,6 +30,11 @@ STK_API int stk_lde(stk_ctx* c, const uint32_t* d_trace, uint64_t steps, uint64_
     coeff_stride = steps;
   }
   STK_TRY(stk_ntt_dev(c, (const fe*)d_trace, steps, trace_stride, coef, coeff_stride, steps, cols, G1, 1, 1));
+  // ext = 8: evals[8K] = trace[K] (the evaluation domain contains the trace domain unshifted), so
+  // the residue-0 coset of the forward transform is copied instead of computed
+  if (ext == 8 && c->is_stark && (const void*)d_trace != (const void*)d_evals)
+    return stk_ntt_dev_r0(c, coef, steps, coeff_stride, (fe*)d_evals, eval_stride, n, cols, G2, (const fe*)d_trace,
+                          trace_stride);
   STK_TRY(stk_ntt_dev(c, coef, steps, coeff_stride, (fe*)d_evals, eval_stride, n, cols, G2, 0, 0));
   return STK_OK;
 }

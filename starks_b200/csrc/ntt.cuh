@@ -56,6 +56,10 @@ struct NttPass {
   int cshift;
   int cs_shift;
   int in_virtual;  // this pass reads the virtual columns (not the first pass of a coset transform)
+  // LDE with N = 8*n_in: the residue-0 coset <w^8> IS the trace domain <G1>, so out[8K] = trace[K]
+  // (starks/stark.py:217-224: no coset shift) and the r = 0 virtual columns need no transform at
+  // all -- their CTAs leave at once (ZS instantiations) and the caller copies the trace in.
+  int cskip0;
   int tw_shift;  // the table is a longer one: entry e lives at W[e << tw_shift]
   int n_tw;
   int j_shift;
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ntt_pass_kernel(const NttPass A, c
   const uint32_t xb = A.c_is_col ? 0u : bx;
   const uint32_t Jcta = ((xb & ((1u << A.nl) - 1u)) << A.sl) | ((xb >> A.nl) << A.sh);
   const uint32_t col0 = A.c_is_col ? (bx << A.logC) : by;
+  if (ZS != 0 && A.cskip0 && !A.c_is_col && (col0 & ((1u << A.cshift) - 1u)) == 0u) return;  // whole CTA
   int a = A.k;
   for (int rd = 0; rd < A.nrounds; ++rd) {
     const int r = A.r[rd];

@@ -321,7 +321,7 @@ static int launch_pass(stk_ctx* c, cudaStream_t s, const NttPass& P, const F&) {
   else if (P.hash_on) return stk_launch_pass_stark_hash(c, s, P);
   else {
   const bool zs = P.zbit < 32 || (P.cshift && !P.in_virtual);  // expansion round / coset scaling on load
-  const bool cf = !zs && P.cshift && P.final_pass;              // interleaved store only
+  const bool cf = !zs && P.cshift && (P.final_pass || P.cskip0);  // interleaved store / skipped r = 0 columns
   if (P.logT > 10)
     return zs ? stk_launch_pass_stark_t11_zs(c, s, P) : cf ? stk_launch_pass_stark_t11_cf(c, s, P) : stk_launch_pass_stark_t11(c, s, P);
   else
@@ -347,9 +347,21 @@ __global__ void dft_generic_kernel(const fe* in, uint64_t n_in, uint64_t in_stri
   fe_store(out + col * out_stride + k, acc);
 }
 
+// out[col][8K] = canonical(r0[col][K]): the residue-0 coset of an 8x extension is the input domain
+__global__ void r0_copy_kernel(const fe* __restrict__ r0, uint64_t r0_stride, fe* __restrict__ out, uint64_t out_stride,
+                               uint64_t ns, uint64_t batch) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= ns * batch) return;
+  const uint64_t col = i / ns, K = i % ns;
+  fe v = fe_load(r0 + col * r0_stride + K);
+  StarkField::canon(v.v);
+  fe_store(out + col * out_stride + 8 * K, v);
+}
+
 static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_in, uint64_t n_in, uint64_t in_stride,
                       fe* d_out, uint64_t out_stride, uint64_t n, uint64_t batch, const fe& root, int inverse,
-                      int scale, const stk_peer_leaf* peer = nullptr, uint32_t* hash_nodes = nullptr) {
+                      int scale, const stk_peer_leaf* peer = nullptr, uint32_t* hash_nodes = nullptr,
+                      const fe* r0 = nullptr, uint64_t r0_stride = 0) {
   if (n == 0 || batch == 0) return STK_OK;
   if (n_in > n) return stk_fail(c, STK_EINDEX, "input length %llu exceeds the order %llu of the root",
                                 (unsigned long long)n_in, (unsigned long long)n);
@@ -360,7 +372,8 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     for (uint64_t b0 = 0; b0 < batch; b0 += 32768) {
       const uint64_t nb = std::min<uint64_t>(32768, batch - b0);
       STK_TRY(ntt_dev_on(c, s, scratch_slot, d_in + b0 * in_stride, n_in, in_stride, d_out + b0 * out_stride,
-                         out_stride, n, nb, root, inverse, scale, nullptr, nullptr));
+                         out_stride, n, nb, root, inverse, scale, nullptr, nullptr, r0 ? r0 + b0 * r0_stride : nullptr,
+                         r0_stride));
     }
     return STK_OK;
   }
@@ -441,7 +454,10 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
     // same on one GPU (2^21: 17.87 ms both) and the coset route measured slower inside the NCCL
     // sharded commit (profiles/r01b_dist_2gpu.txt), so the long transform keeps the expansion round
     const bool fewer_passes = plan.size() < whole.size() || env_int("STK_LDE_COSET", 1) > 1;
-    if (fewer_passes && vb <= 0x7fffffffull && (plan.size() == 1 || vb <= 65535)) {
+    // with the input's own evaluations at hand (r0: the trace of an 8x LDE) the r = 0 coset is a copy:
+    // one eighth of the transform is not computed at all, which pays at every size
+    const bool use_r0 = r0 && n_in * 8 == n && env_int("STK_LDE_R0", 1);
+    if ((fewer_passes || use_r0) && vb <= 0x7fffffffull && (plan.size() == 1 || vb <= 65535)) {
       fe* tmpc = nullptr;
       if (plan.size() > 1) {
         void* t;
@@ -456,12 +472,18 @@ static int ntt_dev_on(stk_ctx* c, cudaStream_t s, int scratch_slot, const fe* d_
         P.tw_shift = P.cs_shift + 3;
         P.cshift = 3;
         P.in_virtual = i > 0;
+        P.cskip0 = use_r0 ? 1 : 0;
         P.zbit = 32;
         if (i == 0) { P.in = d_in; P.in_col_stride = in_stride; P.n_in = (uint32_t)n_in; }
         else { P.in = tmpc; P.in_col_stride = ns; P.n_in = (uint32_t)ns; }
         if (P.final_pass) { P.out = d_out; P.out_col_stride = out_stride; }
         else { P.out = tmpc; P.out_col_stride = ns; }
         STK_TRY(launch_pass<StarkField>(c, s, P, StarkField()));
+      }
+      if (use_r0) {
+        const uint64_t tot = ns * batch;
+        r0_copy_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(r0, r0_stride, d_out, out_stride, ns, batch);
+        STK_CUDA(c, cudaGetLastError());
       }
       return STK_OK;
     }
@@ -556,6 +578,14 @@ int stk_ntt_dev_peer(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stri
                      const fe& root, const stk_peer_leaf& peer) {
   // d_out is never written in peer mode; any distinct non-null pointer keeps the in-place logic off
   return ntt_dev_on(c, c->stream, 0, d_in, n_in, in_stride, (fe*)(uintptr_t)16, n, n, batch, root, 0, 0, &peer);
+}
+
+// Forward transform of coefficient rows whose values on the order-n/8 subgroup are already known
+// (r0: the trace an 8x low-degree extension started from): see NttPass::cskip0.
+int stk_ntt_dev_r0(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, fe* d_out, uint64_t out_stride,
+                   uint64_t n, uint64_t batch, const fe& root, const fe* r0, uint64_t r0_stride) {
+  return ntt_dev_on(c, c->stream, 0, d_in, n_in, in_stride, d_out, out_stride, n, batch, root, 0, 0, nullptr, nullptr,
+                    r0, r0_stride);
 }
 
 int stk_ntt_dev(stk_ctx* c, const fe* d_in, uint64_t n_in, uint64_t in_stride, fe* d_out, uint64_t out_stride,

@@ -212,13 +212,19 @@ class STARK(object):
     d_coef = eng.alloc((3 * w if merged else w) * cs * E)
     if merged and cs > steps:
       eng._check(eng.lib.stk_memset(eng.ctx, d_coef.ptr, 0, 3 * w * cs * E))
-    # construct_trace_polynomials (:27-36): inverse transform over <G1>
-    eng.ntt(d_trace.ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
     # D's evaluations can be taken pointwise from P's wherever Z does not vanish (stk_quotient_eval):
     # then only P and B go through the size-N transform
     pointwise_d = M < N and 2 <= ext <= 16 and os.environ.get("STK_PROOF_POINTWISE", "1") != "0"
-    if not merged or pointwise_d:
-      eng.ntt(d_coef.ptr, steps, cs, d_cols.ptr, N, N, w, G2)            # evaluation of P (:254-256)
+    if (not merged or pointwise_d) and ext == 8 and p == P_STARK:
+      # construct_trace_polynomials (:27-36) and the evaluation of P (:254-256) in one call: with an
+      # 8x blowup the evaluations at every 8th point ARE the trace, so stk_lde copies that coset
+      # instead of computing it (one eighth of the forward transform)
+      eng.lde(d_trace.ptr, steps, steps, ext, w, G2, d_cols.ptr, N, d_coeffs=d_coef.ptr, coeff_stride=cs)
+    else:
+      # construct_trace_polynomials (:27-36): inverse transform over <G1>
+      eng.ntt(d_trace.ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
+      if not merged or pointwise_d:
+        eng.ntt(d_coef.ptr, steps, cs, d_cols.ptr, N, N, w, G2)          # evaluation of P (:254-256)
     if M == N:
       pev_ptr, pev_stride = d_cols.ptr, N
     elif M == steps:

@@ -303,3 +303,30 @@ def test_lde_commit_from_host_trace(eng, oracle):
     for b in (d_tr, ev_a, ev_b, no_a, no_b):
       b.free()
     pin.free()
+
+
+def test_lde_copied_coset_equals_full_transform(eng, oracle, monkeypatch):
+  """With an 8x blowup evals[8K] == trace[K], so stk_lde copies that coset instead of computing it
+  (NttPass::cskip0).  Same evaluations as the full transform (STK_LDE_R0=0) at single-pass, two-pass
+  and three-pass sizes, with strided rows and a ragged column count; and the oracle's where cheap."""
+  rng = np.random.default_rng(123)
+  for logsteps, ncols in ((3, 2), (6, 5), (8, 3), (11, 9), (14, 4), (18, 3), (21, 1)):
+    steps, ext = 1 << logsteps, 8
+    n = steps * ext
+    g2 = pow(7, (P - 1) // n, P)
+    trace = rand_cols(rng, ncols, steps)
+    d_tr = eng.alloc(trace.nbytes).upload(trace)
+    ev_a, ev_b, co = eng.alloc(ncols * n * 32), eng.alloc(ncols * n * 32), eng.alloc(ncols * steps * 32)
+    eng.lde(d_tr.ptr, steps, steps, ext, ncols, g2, ev_a.ptr, n, d_coeffs=co.ptr, coeff_stride=steps)
+    monkeypatch.setenv("STK_LDE_R0", "0")
+    eng.lde(d_tr.ptr, steps, steps, ext, ncols, g2, ev_b.ptr, n)
+    monkeypatch.delenv("STK_LDE_R0")
+    a, b = ev_a.download((ncols, n, 8)), ev_b.download((ncols, n, 8))
+    assert (a == b).all(), logsteps
+    assert (a[:, ::ext] == trace).all()
+    if logsteps <= 14:
+      coeffs = oracle.fft_limbs(P, pow(g2, ext, P), trace, steps, inv=True)
+      assert (co.download((ncols, steps, 8)) == coeffs).all()
+      assert (a == oracle.fft_limbs(P, g2, coeffs, n)).all()
+    for x in (d_tr, ev_a, ev_b, co):
+      x.free()
