@@ -511,10 +511,16 @@ def section_config5(cx, line):
   # the same trace generated on the device (chunk starts from powers of the companion matrix)
   d_w = witness_device(F, [0, 1], psteps, 2, fib, engine=eng)
   eng.sync()
-  t0 = time.perf_counter()
-  d_w2 = witness_device(F, [0, 1], psteps, 2, fib, engine=eng)
-  eng.sync()
-  out["trace_generate_device_s"] = time.perf_counter() - t0
+  best = None
+  for _ in range(3):   # the first repetition may pay a cudaMalloc of the 64 MiB witness buffer
+    t0 = time.perf_counter()
+    d_w2 = witness_device(F, [0, 1], psteps, 2, fib, engine=eng)
+    eng.sync()
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+    if _ < 2:
+      d_w2.free()
+  out["trace_generate_device_s"] = best
   assert (d_w2.download((2, psteps, 8)) == witness).all(), "device trace differs from the host recurrence"
   d_w2.free()
   S = STARK(F, psteps, 8, 2, fib, engine=eng)
