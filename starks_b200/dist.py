@@ -79,6 +79,17 @@ def allgather_roots(root: bytes, group=None, device="cpu"):
   return [bytes(t.cpu().tolist()) for t in out]
 
 
+def allgather_roots_from_nodes(nodes: torch.Tensor, group=None):
+  """Subtree roots straight from the ranks' node buffers (node 1 of each local heap): one
+  all-gather of 32 bytes per rank and ONE device-to-host copy, without the round trip through the
+  host that a root returned by stk_merkle_commit would take."""
+  world, _ = _world(group)
+  out = torch.empty((world, 32), dtype=torch.uint8, device=nodes.device)
+  dist.all_gather_into_tensor(out, nodes[1].contiguous(), group=group)
+  host = out.cpu().numpy()
+  return [host[r].tobytes() for r in range(world)]
+
+
 class ShardedCommit(object):
   """LDE + Merkle commitment with the trace columns sharded over the ranks of `group`."""
 
@@ -219,10 +230,9 @@ class ShardedCommitP2P(object):
     self.hdl.barrier(channel=0)          # nobody still reads the previous commit's rows
     self.eng.lde_p2p(trace.data_ptr(), steps, steps, ext, cl, g2, self.world, self.rank * cl, self.ptrs)
     self.hdl.barrier(channel=1)          # all rows have landed
-    sub_root = self.eng.merkle_commit(self.rows.data_ptr(), self.n_local, self.cols_total, self.n_local,
-                                      self.nodes.data_ptr())
-    roots = allgather_roots(sub_root, self.group, device=trace.device)
-    top = combine_subtree_roots(roots)
+    self.eng.merkle_commit(self.rows.data_ptr(), self.n_local, self.cols_total, self.n_local, self.nodes.data_ptr(),
+                           want_root=False)
+    top = combine_subtree_roots(allgather_roots_from_nodes(self.nodes, self.group))
     return top[1], top
 
 
@@ -283,8 +293,10 @@ class NcclComm(object):
   def rows_barrier(self, engine, channel):
     self.hdl.barrier(channel=channel)     # device-side, on torch's current stream
 
-  def allgather_roots(self, root):
-    return allgather_roots(root, self.group, device=self.device)
+  def commit_roots(self, engine, rows, n_local, ncols, nodes):
+    """Local subtree over `rows` + the roots of every rank's subtree."""
+    engine.merkle_commit(rows.data_ptr(), n_local, ncols, n_local, nodes.data_ptr(), want_root=False)
+    return allgather_roots_from_nodes(nodes, self.group)
 
   def allreduce_bytes(self, buf):
     t = torch.from_numpy(buf).to(self.device)
@@ -325,7 +337,8 @@ class ThreadComm(object):
     engine.sync()
     self.sh.bar.wait()
 
-  def allgather_roots(self, root):
+  def commit_roots(self, engine, rows, n_local, ncols, nodes):
+    root = engine.merkle_commit(rows.data_ptr(), n_local, ncols, n_local, nodes.data_ptr())
     return self._exchange(bytes(root))
 
   def allreduce_bytes(self, buf):
@@ -450,8 +463,7 @@ class ShardedProver(object):
     self.comm.rows_barrier(eng, 0)       # nobody still reads the previous proof's rows
     eng.ntt_p2p(d_coef.at(c0 * cs * 32), cs, cs, N, c1 - c0, G2, G, c0, self.ptrs)
     self.comm.rows_barrier(eng, 1)       # all rows have landed
-    sub = eng.merkle_commit(self.rows.data_ptr(), self.n_local, 3 * w, self.n_local, self.nodes_m.data_ptr())
-    top_m = combine_subtree_roots(self.comm.allgather_roots(sub))
+    top_m = combine_subtree_roots(self.comm.commit_roots(eng, self.rows, self.n_local, 3 * w, self.nodes_m))
     m_root = top_m[1]
     mark("m_root")
     k1, k2, k3, k4 = get_pseudorandom_ks(m_root, 4)
@@ -464,8 +476,7 @@ class ShardedProver(object):
       wP.append(aj * ((k1 + k2 * c) % p) % p)
       wB.append(aj * ((k3 + k4 * c) % p) % p)
     eng.lincomb(self.rows.data_ptr(), self.n_local, 3 * w, self.n_local, wP + wD + wB, self.l_rows.data_ptr())
-    sub_l = eng.merkle_commit(self.l_rows.data_ptr(), self.n_local, 1, self.n_local, self.nodes_l.data_ptr())
-    top_l = combine_subtree_roots(self.comm.allgather_roots(sub_l))
+    top_l = combine_subtree_roots(self.comm.commit_roots(eng, self.l_rows, self.n_local, 1, self.nodes_l))
     l_root = top_l[1]
     mark("l_root")
     positions = get_pseudorandom_indices(l_root, N, 80, exclude_multiples_of=ext)
