@@ -13,18 +13,19 @@ blake = lambda x: blake2s(x).digest()  # starks/merkle_tree.py:1-5
 
 
 def permute4(values: List) -> List:
-  """starks/merkle_tree.py:11-23."""
-  o = []
-  ld4 = len(values) // 4
-  for i in range(ld4):
-    o.extend([values[i], values[i + ld4], values[i + ld4 * 2], values[i + ld4 * 3]])
-  return o
+  """starks/merkle_tree.py:11-23: out[4i + j] = values[i + j*(n//4)] -- the four fold-mates of
+  FRI position i become adjacent leaves.  Elements beyond 4*(n//4) are dropped, as upstream."""
+  q = len(values) // 4
+  out = [None] * (4 * q)
+  for j in range(4):
+    out[j::4] = values[j * q:(j + 1) * q]
+  return out
 
 
 def get_index_in_permuted(x, L):
-  """starks/merkle_tree.py:26-33."""
-  ld4 = L // 4
-  return x // ld4 + 4 * (x % ld4)
+  """starks/merkle_tree.py:26-33: where element x of an L-element list sits after permute4."""
+  j, i = divmod(x, L // 4)
+  return 4 * i + j
 
 
 def _serialise(L):
@@ -63,28 +64,28 @@ def merkelize(L, engine=None) -> List[bytes]:
 
 
 def mk_branch(tree, index: int):
-  """A branch of the merkle tree is a list (starks/merkle_tree.py:59-68)."""
-  index = get_index_in_permuted(index, len(tree) // 2)
-  index += len(tree) // 2
-  o = [tree[index]]
-  while index > 1:
-    o.append(tree[index ^ 1])
-    index //= 2
-  return o
+  """starks/merkle_tree.py:59-68: [leaf, sibling, sibling of the parent, ...] up to (excluding)
+  the root, for the leaf that held element `index` before permute4."""
+  n = len(tree) // 2
+  node = n + get_index_in_permuted(index, n)
+  path = [tree[node]]
+  while node > 1:
+    path.append(tree[node ^ 1])
+    node >>= 1
+  return path
 
 
 def verify_branch(root, index, proof, output_as_int=False):
-  """Verifies the proof and returns the leaf on the branch (starks/merkle_tree.py:71-86)."""
-  index = get_index_in_permuted(index, 2**len(proof) // 2)
-  index += 2**len(proof) // 2
-  v = proof[0]
-  for p in proof[1:]:
-    if index % 2:
-      v = blake(p + v)
-    else:
-      v = blake(v + p)
-    index //= 2
-  assert v == root
+  """starks/merkle_tree.py:71-86: re-hashes the branch (hashlib) and returns its leaf; raises
+  AssertionError when it does not lead to `root`.  A branch of k entries belongs to a tree of
+  2^(k-1) leaves."""
+  n = (1 << len(proof)) >> 1
+  node = n + get_index_in_permuted(index, n)
+  acc = proof[0]
+  for sibling in proof[1:]:
+    acc = blake(sibling + acc) if node & 1 else blake(acc + sibling)
+    node >>= 1
+  assert acc == root
   return int.from_bytes(proof[0], "big") if output_as_int else proof[0]
 
 
@@ -120,11 +121,6 @@ def merkelize_polynomial_evaluations(dims, polynomial_evals, engine=None):
 
 
 def unpack_merkle_leaf(leaf: bytes, dims: int, num_polys: int) -> List[bytes]:
-  """starks/merkle_tree.py:121-147."""
-  vals = []
-  for poly_ind in range(num_polys):
-    for dim in range(dims):
-      start_index = 32 * (poly_ind * dims + dim)
-      end_index = 32 * (poly_ind * dims + dim + 1)
-      vals.append(leaf[start_index:end_index])
-  return vals
+  """starks/merkle_tree.py:121-147: the 32-byte values of a leaf made by
+  merkelize_polynomial_evaluations, polynomial-major, dimension-minor."""
+  return [leaf[32 * k:32 * (k + 1)] for k in range(num_polys * dims)]

@@ -28,13 +28,13 @@ blake = lambda x: blake2s(x).digest()
 
 
 def get_pseudorandom_ks(m_root: bytes, num: int):
-  """starks/stark.py:106-126 (the salts are the ASCII strings b'0x01'...)."""
-  if 0 <= num and num <= 4:
-    byte_list = [b"0x01", b"0x02", b"0x03", b"0x04"]
-    return [int.from_bytes(blake(m_root + byte_list[ind]), "big") for ind in range(num)]
-  elif num < 10:
-    byte_list = [("0x0%s" % str(i)).encode("UTF-8") for i in range(num)]
-    return [int.from_bytes(blake(m_root + byte_list[ind]), "big") for ind in range(num)]
+  """starks/stark.py:106-126: k_i = BLAKE2s(m_root | salt_i) as integers.  The salts are ASCII
+  strings: b'0x01'.. for num <= 4, b'0x00'.. (a different numbering) for 5 <= num < 10, and the
+  reference returns None for ten or more."""
+  if num < 0 or num >= 10:
+    return None
+  first = 1 if num <= 4 else 0
+  return [int.from_bytes(blake(m_root + b"0x0%d" % (first + i)), "big") for i in range(num)]
 
 
 def _interp2(p, x0, x1, y0, y1):

@@ -42,17 +42,21 @@ def get_power_cycle(r, field, engine=None):
 
 
 def get_pseudorandom_indices(entropy, modulus, count, exclude_multiples_of=0):
-  """starks/utils.py:60-90."""
+  """starks/utils.py:60-90: `count` indices below `modulus` from the 4-byte big-endian words of
+  entropy | H(last 32 bytes) | H(...) ...; with exclude_multiples_of = e the draw is taken over the
+  positions that are NOT multiples of e (x -> x + 1 + x // (e - 1))."""
   assert modulus < 2**24
-  data = entropy
-  while len(data) < 4 * count:
-    data += blake(data[-32:])
-  if exclude_multiples_of == 0:
-    return [int.from_bytes(data[i:i + 4], "big") % modulus for i in range(0, count * 4, 4)]
-  real_modulus = modulus * (exclude_multiples_of - 1) // exclude_multiples_of
-  o = [int.from_bytes(data[i:i + 4], "big") % real_modulus for i in range(0, count * 4, 4)]
-  return [x + 1 + x // (exclude_multiples_of - 1) for x in o]
+  stream = bytes(entropy)
+  while len(stream) < 4 * count:            # entropy expansion: chain BLAKE2s over the last digest
+    stream += blake(stream[-32:])
+  words = [int.from_bytes(stream[4 * k:4 * k + 4], "big") for k in range(count)]
+  e = exclude_multiples_of
+  if not e:
+    return [w % modulus for w in words]
+  allowed = modulus * (e - 1) // e          # how many positions are not multiples of e
+  return [x + 1 + x // (e - 1) for x in (w % allowed for w in words)]
 
 
 def is_a_power_of_2(x):
-  return True if x == 1 else False if x % 2 else is_a_power_of_2(x // 2)
+  """starks/utils.py:93-94 (x >= 1)."""
+  return x & (x - 1) == 0
