@@ -349,19 +349,37 @@ def section_config3(cx, line, reps=4):
     del d_nodes
     torch.cuda.empty_cache()
     mine = trace[rank * cl:(rank + 1) * cl].contiguous()
+    # this rank's LDE alone (column-sharded evaluations, no exchange), with and without the copied coset
+    ev_loc = torch.empty((cl, n, 8), dtype=torch.int32, device=dev)
+    for tag, env in (("lde_only_ms", None), ("lde_only_full_transform_ms", "0")):
+      if env is not None:
+        os.environ["STK_LDE_R0"] = env
+      try:
+        eng.lde(mine.data_ptr(), steps, steps, ext, cl, g2, ev_loc.data_ptr(), n)
+        out[tag], _ = cx.timed(lambda: eng.lde(mine.data_ptr(), steps, steps, ext, cl, g2, ev_loc.data_ptr(), n), reps)
+      finally:
+        if env is not None:
+          del os.environ["STK_LDE_R0"]
+    del ev_loc
+    torch.cuda.empty_cache()
     sc = sd.ShardedCommit(eng)
     for _ in range(2):
       r = sc.lde_commit(mine, ext, g2)
     ok_nccl = cx.all_true(r[0] == want_root)
     del r
-    cx.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    per_call = []
+    for _ in range(reps + 1):
+      cx.barrier()
+      t0 = time.perf_counter()
       r = sc.lde_commit(mine, ext, g2)
-    torch.cuda.synchronize()
-    out["nccl_all_to_all_ms"] = cx.tmax((time.perf_counter() - t0) / reps * 1e3)
+      torch.cuda.synchronize()
+      per_call.append((time.perf_counter() - t0) * 1e3)
+      del r                                  # evaluations, rows and nodes of this call (6 GiB) go back first
+    per_call = sorted(per_call[1:])
+    out["nccl_all_to_all_ms"] = cx.tmax(per_call[len(per_call) // 2])      # median call, max over ranks
+    out["nccl_all_to_all_ms_per_call"] = [round(x, 2) for x in per_call]
     out["nccl_root_equals_one_gpu_root"] = ok_nccl
-    del r
+    out["nccl_host_timeline_ms"] = getattr(sc, "timings", None)
     torch.cuda.empty_cache()
     parity = parity and ok_nccl
     best_n = out["nccl_all_to_all_ms"]

@@ -100,22 +100,31 @@ class ShardedCommit(object):
   def lde_commit(self, trace: torch.Tensor, ext: int, g2: int):
     """trace: (cols_local, steps, 8) int32 CUDA tensor (this rank's columns).
     Returns (root, top_nodes, evals_local, rows_all_columns, local_nodes)."""
+    import time
     cl, steps, _ = trace.shape
     n = steps * ext
     dev = trace.device
     _adopt_stream(self.eng, trace)
+    marks = [("start", time.perf_counter())]
     evals = torch.empty((cl, n, 8), dtype=torch.int32, device=dev)
+    marks.append(("alloc_evals", time.perf_counter()))
     self.eng.lde(trace.data_ptr(), steps, steps, ext, cl, g2, evals.data_ptr(), n)
+    marks.append(("lde_enqueued", time.perf_counter()))
     if self.world == 1:
       nodes = torch.empty((n, 32), dtype=torch.uint8, device=dev)
       root = self.eng.merkle_commit(evals.data_ptr(), n, cl, n, nodes.data_ptr())
       return root, {1: root}, evals, evals, nodes
     rows = exchange_leaf_rows(evals, self.group)            # (cols_total, n/G, 8)
+    marks.append(("exchange_enqueued", time.perf_counter()))
     n_local = n // self.world
     nodes = torch.empty((n_local, 32), dtype=torch.uint8, device=dev)
     sub_root = self.eng.merkle_commit(rows.data_ptr(), n_local, rows.shape[0], n_local, nodes.data_ptr())
+    marks.append(("subtree_root_on_host", time.perf_counter()))
     roots = allgather_roots(sub_root, self.group, device=dev)
+    marks.append(("roots_gathered", time.perf_counter()))
     top = combine_subtree_roots(roots)
+    # host-side timeline of the last call (ms since entry): where the calling thread was held up
+    self.timings = {name: round((t - marks[0][1]) * 1e3, 3) for name, t in marks[1:]}
     return top[1], top, evals, rows, nodes
 
 
