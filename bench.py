@@ -65,6 +65,13 @@ NCU_FMAHEAVY_ACTIVE_PCT = (72.3, 70.2)   # first pass, final pass
 WORKLOAD = "forward NTT, %d columns x 2^20 per GPU, p = 2^256-351*2^32+1 (BASELINE configs[1] at its headline size)"
 
 
+def bench_config(cols, world):
+  """The `config` object of the line: identical for our arm and for the reference arm."""
+  return {"workload": WORKLOAD % cols, "cols_per_gpu": cols, "log2_n": LOGN,
+          "l2_policy": "inputs (2 GiB) exceed L2, no flush",
+          "parallelism": "column-sharded x%d, no collective (configs 3 and 4 in the same line use the exchange paths)" % world}
+
+
 def host_threads():
   """Threads this process may run on.  Not OMP_NUM_THREADS: torchrun exports it as 1."""
   try:
@@ -707,11 +714,11 @@ def run_reference(args, rank, world):
       "impl": "reference", "metric": "ntt_melem_per_s_2^20", "value": val, "unit": "Melem/s", "n_gpus": args.gpus,
       "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic",
-      "config": {"workload": WORKLOAD % args.cols,
-                 "sample": "each step transforms %d of the columns (one per host thread)" % cols,
-                 "note": "the reference is pure Python and single-threaded (fft_1d at 2^20 = 74 s per column, "
-                         "BASELINE.md); this arm is the C oracle port of fft_1d on %d host threads "
-                         "(os.sched_getaffinity, not OMP_NUM_THREADS)" % threads},
+      "config": bench_config(args.cols, max(1, args.gpus)),
+      "reference_note": "the reference is pure Python and single-threaded (fft_1d at 2^20 = 74 s per column, "
+                        "BASELINE.md); this arm is the C oracle port of fft_1d on %d host threads "
+                        "(os.sched_getaffinity, not OMP_NUM_THREADS); each step is a bounded sample of the "
+                        "workload: %d of its columns, one per thread" % (threads, cols),
       "cpu_baseline": {"value": val, "unit": "Melem/s", "cores": threads, "kind": "port",
                        "sample": "%d columns x 2^20 per step, %d steps after %d warm-up" % (cols, steps, warm)},
       "e2e": {"value": val, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -867,9 +874,7 @@ def main():
         "metric": "ntt_melem_per_s_2^20", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic",
-        "config": {"workload": WORKLOAD % cols,
-                   "cols_per_gpu": cols, "log2_n": LOGN, "l2_policy": "inputs (2 GiB) exceed L2, no flush",
-                   "parallelism": "column-sharded x%d, no collective (configs 3 and 4 below use the exchange paths)" % world},
+        "config": bench_config(cols, world),
         "clocks": clocks,
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "int32", "achieved": int_achieved / 1e3, "peak": (int_peak or 0) / 1e3, "unit": "Tops/s",
