@@ -181,13 +181,57 @@ __global__ void __launch_bounds__(128) verify_branches_kernel(const uint32_t* __
   ok[r] = diff == 0;
 }
 
-// Power-of-two trees: nodes [1, np/2) have node children; levels go bottom-up, the last
-// (at most 1024-node) levels run inside one CTA.
+// D consecutive levels in one launch: CTA b owns the subtree under node R = roots + b of the level
+// with `roots` nodes, stages the subtree's 2^D already-computed descendants (nodes R*2^D ...) in
+// shared memory and writes the D levels above them.  Used where a level is too small to fill the
+// GPU (< 2^16 nodes): there a launch per level costs more than its compressions (FRI layers,
+// upper halves of every tree).
+__global__ void __launch_bounds__(64) merkle_mid_kernel(uint32_t* __restrict__ nodes, uint32_t roots, int D) {
+  __shared__ uint4 sm[2 * 128];                       // up to 2^7 nodes of two uint4 each
+  const uint64_t R = (uint64_t)roots + blockIdx.x;
+  const uint32_t nin = 1u << D;
+  const uint4* src = reinterpret_cast<const uint4*>(nodes + 8 * (R << D));
+  for (uint32_t i = threadIdx.x; i < 2 * nin; i += blockDim.x) sm[i] = src[i];
+  __syncthreads();
+  for (int lv = 1; lv <= D; ++lv) {
+    const uint32_t cnt = nin >> lv;                   // nodes of this level inside the subtree
+    const uint32_t t = threadIdx.x;
+    uint32_t h[8];
+    if (t < cnt) {
+      const uint4 a = sm[4 * t], b = sm[4 * t + 1], cc = sm[4 * t + 2], d = sm[4 * t + 3];
+      uint32_t m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z, d.w};
+      b2s_init(h);
+      b2s_compress(h, m, 64u, true);
+    }
+    __syncthreads();                                  // every pair is read before any slot is reused
+    if (t < cnt) {
+      const uint4 lo4 = make_uint4(h[0], h[1], h[2], h[3]), hi4 = make_uint4(h[4], h[5], h[6], h[7]);
+      sm[2 * t] = lo4;
+      sm[2 * t + 1] = hi4;
+      uint4* dst = reinterpret_cast<uint4*>(nodes + 8 * ((R << (D - lv)) + t));
+      dst[0] = lo4;
+      dst[1] = hi4;
+    }
+    __syncthreads();
+  }
+}
+
+// Power-of-two trees: nodes [1, np/2) have node children; levels go bottom-up.  Levels of 2^16
+// nodes and more get one launch each; below that one launch covers up to 7 levels in shared
+// memory, and the last (at most 512-node) levels run inside one CTA.
 int reduce_levels(stk_ctx* c, uint32_t* nodes, uint64_t np) {
   if (np < 4) return STK_OK;
   uint64_t lo = np >> 2;
-  for (; lo >= 1024; lo >>= 1)
+  for (; lo >= 65536; lo >>= 1)
     merkle_level_kernel<<<(unsigned)((lo + 255) / 256), 256, 0, c->stream>>>(nodes, lo, lo);
+  while (lo >= 1024) {                                // lo < 2^16: 2..7 levels at once, down to a 512-node level
+    int loglo = 0;
+    while ((1ull << loglo) < lo) ++loglo;
+    const int D = loglo - 8 > 7 ? 7 : loglo - 8;      // levels lo, lo/2, ..., lo >> (D-1)
+    const uint32_t roots = (uint32_t)(lo >> (D - 1));
+    merkle_mid_kernel<<<roots, 64, 0, c->stream>>>(nodes, roots, D);
+    lo = roots >> 1;
+  }
   if (lo >= 1) merkle_top_kernel<<<1, 512, 0, c->stream>>>(nodes, (uint32_t)(2 * lo), np);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;

@@ -466,9 +466,9 @@ class ShardedProver(object):
     else:
       d_trace = eng.alloc(w * steps * 32).upload(tr, wait=False)
       last_rows = tr[:, -1, :]
-    d_coef, cs = S.coefficient_rows(eng, d_trace.ptr, boundary, limbs_to_ints(last_rows))
-    mark("coefficients")
     c0, c1 = split_columns(3 * w, G)[rank]
+    d_coef, cs = S.coefficient_rows(eng, d_trace.ptr, boundary, limbs_to_ints(last_rows), want=range(c0, c1))
+    mark("coefficients")
     self.comm.rows_barrier(eng, 0)       # nobody still reads the previous proof's rows
     eng.ntt_p2p(d_coef.at(c0 * cs * 32), cs, cs, N, c1 - c0, G2, G, c0, self.ptrs)
     self.comm.rows_barrier(eng, 1)       # all rows have landed
@@ -489,13 +489,7 @@ class ShardedProver(object):
     l_root = top_l[1]
     mark("l_root")
     positions = get_pseudorandom_indices(l_root, N, 80, exclude_multiples_of=ext)
-    mb, lb = self._branches([
-        (self.rows, 3 * w, self.nodes_m, top_m, [x for pos in positions for x in (pos, (pos + ext) % N)]),
-        (self.l_rows, 1, self.nodes_l, top_l, positions)])
-    branches = []
-    for i in range(len(positions)):
-      branches += [mb[2 * i], mb[2 * i + 1], lb[i]]
-    mark("spot_checks")
+    # (the spot-check branches are cut together with FRI layer 0's below: one exchange for both)
     # FRI layer 0 (fri.py:217-256) on the sharded l, the rest on rank 0
     maxdeg = steps * S.get_degree()
     assert maxdeg > 16, "the sharded prover needs at least one FRI fold layer"
@@ -506,8 +500,14 @@ class ShardedProver(object):
     self.comm.allgather_column(eng, self.column, self.col_local)
     root2 = eng.merkle_commit(self.column.data_ptr(), q, 1, q, self.nodes2.data_ptr())
     ys = get_pseudorandom_indices(root2, q, 40, exclude_multiples_of=ext)
-    (lb0,) = self._branches([(self.l_rows, 1, self.nodes_l, top_l, [y + q * j for y in ys for j in range(4)])])
-    mark("fri_layer0")
+    mb, lb, lb0 = self._branches([
+        (self.rows, 3 * w, self.nodes_m, top_m, [x for pos in positions for x in (pos, (pos + ext) % N)]),
+        (self.l_rows, 1, self.nodes_l, top_l, positions),
+        (self.l_rows, 1, self.nodes_l, top_l, [y + q * j for y in ys for j in range(4)])])
+    branches = []
+    for i in range(len(positions)):
+      branches += [mb[2 * i], mb[2 * i + 1], lb[i]]
+    mark("fri_layer0_and_branches")
     proof = None
     if rank == 0:
       cb = eng.merkle_paths(self.column.data_ptr(), q, 1, q, self.nodes2.data_ptr(), ys)

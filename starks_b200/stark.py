@@ -102,16 +102,21 @@ class STARK(object):
     h_exp = np.asarray(mono_exp, dtype=np.uint8).reshape(nm, w) if nm else np.zeros((0, w), np.uint8)
     return nm, h_out, h_coef, h_exp
 
-  def coefficient_rows(self, eng, d_trace_ptr, boundary, out_vals):
+  def coefficient_rows(self, eng, d_trace_ptr, boundary, out_vals, want=None):
     """The 3w polynomials mk_proof commits to -- P_1..P_w (stark.py:27-36), D_1..D_w (:38-78),
     B_1..B_w (:80-104), in the leaf order of :247 -- as COEFFICIENT rows on the device: returns
     (buffer, row stride cs), row r at byte r*cs*32, zero-padded to cs >= deg + 1.  The sharded
     prover (dist.ShardedProver) evaluates slices of these rows on different GPUs; mk_proof itself
-    takes shortcuts (pointwise quotients) that this form does not need."""
+    takes shortcuts (pointwise quotients) that this form does not need.
+    want: the rows the caller will read (global row numbers 0..3w-1; default all).  Only those --
+    and what they depend on -- are computed: a rank that evaluates one column of a Fibonacci proof
+    runs one or two transforms of size `steps` here instead of four."""
     p = self.field.p
     w, steps, ext, N = self.width, self.steps, self.extension_factor, self.precision
     G2, last = int(self.G2), int(self.last_step_position)
+    G1 = pow(G2, ext, p)
     E = 32
+    want = set(range(3 * w)) if want is None else set(int(c) for c in want)
     nm, h_out, h_coef, h_exp = self._monomial_arrays()
     mult = 1
     while mult < max(self.get_degree(), 1):
@@ -119,41 +124,64 @@ class STARK(object):
     M = min(N, steps * mult)
     GM = pow(G2, N // M, p)
     cs = M
+    want_d = sorted(c - w for c in want if w <= c < 2 * w)
+    want_b = sorted(c - 2 * w for c in want if c >= 2 * w)
+    # P's coefficients: for its own rows, for B_j, and -- unless the constraint subgroup is the trace
+    # domain itself -- for every column (C_j needs all of P on that subgroup)
+    need_p = set(c for c in want if c < w) | set(want_b)
+    if want_d and M != steps:
+      need_p = set(range(w))
     d_coef = eng.alloc(3 * w * cs * E)
     eng._check(eng.lib.stk_memset(eng.ctx, d_coef.ptr, 0, 3 * w * cs * E))
-    eng.ntt(d_trace_ptr, steps, steps, d_coef.ptr, cs, steps, w, pow(G2, ext, p), inverse=True)
-    d_t1, d_t2 = eng.alloc(w * M * E), eng.alloc(w * M * E)
-    if M == steps:
-      pev_ptr, pev_stride = d_trace_ptr, steps     # P_j on <G1> is the witness column itself
+    if len(need_p) == w:
+      eng.ntt(d_trace_ptr, steps, steps, d_coef.ptr, cs, steps, w, G1, inverse=True)
     else:
-      eng.ntt(d_coef.ptr, steps, cs, d_t2.ptr, M, M, w, GM)
-      pev_ptr, pev_stride = d_t2.ptr, M
-    eng._check(eng.lib.stk_constraint_eval(eng.ctx, pev_ptr, M, M // steps, w, pev_stride, h_out.ctypes.data,
-                                           h_coef.ctypes.data, h_exp.ctypes.data, nm, d_t1.ptr, M))
-    d_t3 = eng.alloc(w * M * E)
-    eng.ntt(d_t1.ptr, M, M, d_t3.ptr, M, M, w, GM, inverse=True)
+      for j in sorted(need_p):
+        eng.ntt(d_trace_ptr + j * steps * E, steps, steps, d_coef.at(j * cs * E), cs, steps, 1, G1, inverse=True)
+    held = []
     bad = ctypes.c_uint32(0)
     last_l, one_l = int_to_limbs(last), int_to_limbs(1)
     u32p = ctypes.POINTER(ctypes.c_uint32)
-    for j in range(w):
-      eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t3.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
-                                        d_coef.at((w + j) * cs * E), ctypes.byref(bad)))
-      assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
-    interps = []
-    for j in range(w):
-      (_, _, input_value) = boundary[j]
-      interps += _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
-    d_i = eng.alloc(2 * w * E).upload(ints_to_limbs(interps))
-    for j in range(w):
-      a = d_coef.at((2 * w + j) * cs * E)
-      eng._check(eng.lib.stk_memcpy_d2d(eng.ctx, a, d_coef.at(j * cs * E), steps * E))
-      eng._check(eng.lib.stk_vec_op(eng.ctx, 1, a, d_i.at(2 * j * E), a, 2))
-      q1 = d_t1.at(j * steps * E)
-      eng._check(eng.lib.stk_div_linear(eng.ctx, a, steps, one_l.ctypes.data_as(u32p), 1, q1))
-      eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
-      eng._check(eng.lib.stk_memset(eng.ctx, a + (steps - 2) * E, 0, 2 * E))
-    eng.sync()   # d_i and the scratch rows go back to the pool
-    for b in (d_t1, d_t2, d_t3, d_i):
+    d_t1 = eng.alloc(w * M * E)
+    held.append(d_t1)
+    if want_d:
+      if M == steps:
+        pev_ptr, pev_stride = d_trace_ptr, steps     # P_j on <G1> is the witness column itself
+      else:
+        d_t2 = eng.alloc(w * M * E)
+        held.append(d_t2)
+        eng.ntt(d_coef.ptr, steps, cs, d_t2.ptr, M, M, w, GM)
+        pev_ptr, pev_stride = d_t2.ptr, M
+      eng._check(eng.lib.stk_constraint_eval(eng.ctx, pev_ptr, M, M // steps, w, pev_stride, h_out.ctypes.data,
+                                             h_coef.ctypes.data, h_exp.ctypes.data, nm, d_t1.ptr, M))
+      d_t3 = eng.alloc(w * M * E)
+      held.append(d_t3)
+      if len(want_d) == w:
+        eng.ntt(d_t1.ptr, M, M, d_t3.ptr, M, M, w, GM, inverse=True)
+      else:
+        for j in want_d:
+          eng.ntt(d_t1.at(j * M * E), M, M, d_t3.at(j * M * E), M, M, 1, GM, inverse=True)
+      for j in want_d:
+        eng._check(eng.lib.stk_quotient_z(eng.ctx, d_t3.at(j * M * E), M, steps, last_l.ctypes.data_as(u32p),
+                                          d_coef.at((w + j) * cs * E), ctypes.byref(bad)))
+        assert bad.value == 0, "constraint polynomial is not divisible by Z (stark.py:74-75)"
+    if want_b:
+      interps = []
+      for j in range(w):
+        (_, _, input_value) = boundary[j]
+        interps += _interp2(p, 1, last, element_to_int(input_value) % p, out_vals[j])
+      d_i = eng.alloc(2 * w * E).upload(ints_to_limbs(interps))
+      held.append(d_i)
+      for j in want_b:
+        a = d_coef.at((2 * w + j) * cs * E)
+        eng._check(eng.lib.stk_memcpy_d2d(eng.ctx, a, d_coef.at(j * cs * E), steps * E))
+        eng._check(eng.lib.stk_vec_op(eng.ctx, 1, a, d_i.at(2 * j * E), a, 2))
+        q1 = d_t1.at(j * steps * E)      # free again: its last reader is already enqueued on the stream
+        eng._check(eng.lib.stk_div_linear(eng.ctx, a, steps, one_l.ctypes.data_as(u32p), 1, q1))
+        eng._check(eng.lib.stk_div_linear(eng.ctx, q1, steps - 1, last_l.ctypes.data_as(u32p), steps, a))
+        eng._check(eng.lib.stk_memset(eng.ctx, a + (steps - 2) * E, 0, 2 * E))
+    eng.sync()   # the scratch rows go back to the pool
+    for b in held:
       b.free()
     return d_coef, cs
 
