@@ -46,7 +46,9 @@ int stk_init(int device, stk_ctx** ctx);
 void stk_destroy(stk_ctx* ctx);
 const char* stk_last_error(stk_ctx* ctx);
 /* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = the
- * context's own stream. */
+ * context's own stream.  Switching to a different stream first drains the old one (its work may
+ * still read cached tables / scratch the new stream's calls are free to evict); setting the
+ * stream already in use costs nothing. */
 int stk_set_stream(stk_ctx* ctx, void* cuda_stream);
 int stk_sync(stk_ctx* ctx);
 /* Modulus of IntegersModP(p) (starks/modp.py:25-106).  p = 2^256 - 351*2^32 + 1 selects

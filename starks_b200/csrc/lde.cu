@@ -5,6 +5,7 @@
 // no coset shift in the reference: the evaluation domain is the subgroup <G2> itself, so
 // evals[i*ext] == trace[i].
 #include <algorithm>
+#include <vector>
 #include "ctx.h"
 
 using namespace stk;
@@ -117,20 +118,32 @@ STK_API int stk_lde_commit_host(stk_ctx* c, const uint32_t* h_trace, uint64_t st
     return STK_EINVAL;
   const uint64_t n = steps * ext;
   const uint64_t col_bytes = steps * sizeof(fe);
-  uint64_t chunk = std::max<uint64_t>(1, ((uint64_t)32 << 20) / col_bytes);
-  chunk = std::min(chunk, cols);
+  // Group sizes grow geometrically (x1.5): only the FIRST group's copy is exposed, so it is small
+  // (~16 MiB), and a column uploads faster than it transforms (PCIe ~50 GB/s against ~0.28 ms per
+  // 2^18-step column), so a group up to 1.7x the previous one still arrives in time; larger
+  // groups keep the per-launch overheads of the transforms down.  Capped at 128 MiB per slot.
+  const uint64_t first = std::max<uint64_t>(1, ((uint64_t)16 << 20) / col_bytes);
+  const uint64_t cap = std::max<uint64_t>(first, ((uint64_t)128 << 20) / col_bytes);
+  std::vector<uint64_t> groups;
+  for (uint64_t done = 0, g = first; done < cols; g = std::min(cap, g + (g + 1) / 2)) {
+    const uint64_t nb = std::min(g, cols - done);
+    groups.push_back(nb);
+    done += nb;
+  }
+  const uint64_t slot_cols = std::min(cap, cols);
   void* st;
-  STK_TRY(stk_scratch(c, 11, 2 * chunk * col_bytes, &st));
-  fe* slot[2] = {(fe*)st, (fe*)st + chunk * steps};
+  STK_TRY(stk_scratch(c, 11, 2 * slot_cols * col_bytes, &st));
+  fe* slot[2] = {(fe*)st, (fe*)st + slot_cols * steps};
   cudaStream_t cp = c->copy_streams[0];
   // the staging slots may still be read by transforms of an earlier call on the compute stream
   STK_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   STK_CUDA(c, cudaStreamWaitEvent(cp, c->ev[0], 0));
-  int k = 0;
-  for (uint64_t b0 = 0; b0 < cols; b0 += chunk, k ^= 1) {
-    const uint64_t nb = std::min(chunk, cols - b0);
+  uint64_t b0 = 0;
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const int k = (int)(gi & 1);
+    const uint64_t nb = groups[gi];
     cudaEvent_t up = c->ev[1 + k], done = c->ev[3 + k];
-    if (b0 >= 2 * chunk) STK_CUDA(c, cudaStreamWaitEvent(cp, done, 0));   // slot k's previous group is transformed
+    if (gi >= 2) STK_CUDA(c, cudaStreamWaitEvent(cp, done, 0));   // slot k's previous group is transformed
     if (trace_stride == steps)
       STK_CUDA(c, cudaMemcpyAsync(slot[k], h_trace + b0 * trace_stride * 8, nb * col_bytes, cudaMemcpyHostToDevice, cp));
     else
@@ -141,6 +154,7 @@ STK_API int stk_lde_commit_host(stk_ctx* c, const uint32_t* h_trace, uint64_t st
     STK_TRY(stk_lde(c, (const uint32_t*)slot[k], steps, steps, ext, nb, g2, nullptr, 0,
                     d_evals + b0 * eval_stride * 8, eval_stride));
     STK_CUDA(c, cudaEventRecord(done, c->stream));
+    b0 += nb;
   }
   return stk_merkle_commit(c, d_evals, n, cols, eval_stride, d_nodes, h_root);
 }

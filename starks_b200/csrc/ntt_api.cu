@@ -82,7 +82,13 @@ extern "C" __attribute__((visibility("default"))) const char* stk_last_error(stk
 
 extern "C" __attribute__((visibility("default"))) int stk_set_stream(stk_ctx* c, void* s) {
   if (!c) return STK_EINVAL;
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  cudaStream_t next = s ? (cudaStream_t)s : c->own_stream;
+  if (next != c->stream) {
+    // work enqueued on the old stream may still read cached tables and scratch buffers that the new
+    // stream's calls are free to evict or regrow: drain it once, at the switch
+    STK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = next;
+  }
   return STK_OK;
 }
 
