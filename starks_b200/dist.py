@@ -239,10 +239,47 @@ class ShardedCommitP2P(object):
     self.hdl.barrier(channel=0)          # nobody still reads the previous commit's rows
     self.eng.lde_p2p(trace.data_ptr(), steps, steps, ext, cl, g2, self.world, self.rank * cl, self.ptrs)
     self.hdl.barrier(channel=1)          # all rows have landed
+    return self._commit_rows()
+
+  def _commit_rows(self):
     self.eng.merkle_commit(self.rows.data_ptr(), self.n_local, self.cols_total, self.n_local, self.nodes.data_ptr(),
                            want_root=False)
     top = combine_subtree_roots(allgather_roots_from_nodes(self.nodes, self.group))
     return top[1], top
+
+  def lde_commit_host(self, h_trace: torch.Tensor, d_stage: torch.Tensor, ext: int, g2: int):
+    """The same commit with this rank's columns in pinned HOST memory (h_trace: (cols_local, steps,
+    8) int32 CPU tensor, d_stage: a device tensor of the same shape): columns are uploaded in
+    geometrically growing groups on a side stream while the previous group is transformed and
+    scattered, so only the first group's copy is exposed (the end-to-end form of the metric)."""
+    cl, steps, _ = h_trace.shape
+    assert steps * ext == self.n and cl * self.world == self.cols_total and d_stage.shape == h_trace.shape
+    _adopt_stream(self.eng, d_stage)
+    main = torch.cuda.current_stream(d_stage.device)
+    if not hasattr(self, "_copy_stream"):
+      self._copy_stream = torch.cuda.Stream(device=d_stage.device)
+    side = self._copy_stream
+    side.wait_stream(main)               # d_stage may still be read by the previous call's transforms
+    groups, done, g = [], 0, max(1, cl // 8)
+    while done < cl:
+      nb = min(g, cl - done)
+      groups.append((done, nb))
+      done += nb
+      g = g + (g + 1) // 2
+    events = []
+    with torch.cuda.stream(side):
+      for c0, nb in groups:
+        d_stage[c0:c0 + nb].copy_(h_trace[c0:c0 + nb], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        events.append(ev)
+    self.hdl.barrier(channel=0)
+    for (c0, nb), ev in zip(groups, events):
+      main.wait_event(ev)
+      self.eng.lde_p2p(d_stage[c0:c0 + nb].data_ptr(), steps, steps, ext, nb, g2, self.world, self.rank * cl + c0,
+                       self.ptrs)
+    self.hdl.barrier(channel=1)
+    return self._commit_rows()
 
 
 # ---------------------------------------------------------------- one proof over all ranks

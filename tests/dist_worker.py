@@ -131,6 +131,12 @@ for steps, ncols in ((1 << 12, 8),) + (((1 << 18, 64),) if full else ()):
   for rep in range(2):
     root_p, _ = scp.lde_commit(mine, ext, g2)
     assert root_p == want_root, "sharded commit (fused P2P) root mismatch (rep %d)" % rep
+  # the same commit from a pinned host trace, upload pipelined with the per-group transforms
+  h_mine = mine.cpu().pin_memory()
+  stage = torch.empty_like(mine)
+  for rep in range(2):
+    root_h, _ = scp.lde_commit_host(h_mine, stage, ext, g2)
+    assert root_h == want_root, "sharded commit from a host trace: root mismatch (rep %d)" % rep
   torch.cuda.synchronize()
   # the rows a rank received are exactly a local tree's rows in permute4 order
   q = n // 4
