@@ -434,6 +434,7 @@ def section_config3(cx, line, reps=4):
   line["lde_merkle_commit_ms"] = best
   line["lde_merkle_commit_e2e_ms"] = out.get("e2e_ms")
   line["lde_merkle_commit_parity_ok"] = bool(parity)
+  line["lde_merkle_commit_strong_scaling_efficiency"] = out.get("strong_scaling_efficiency", 1.0)
   line["lde_merkle_commit"] = out
   torch.cuda.empty_cache()
 
@@ -510,6 +511,7 @@ def section_config4(cx, line, reps=4):
   line["ntt_2^26_ms"] = best
   line["ntt_2^26_melem_per_s"] = n / (best * 1e-3) / 1e6
   line["ntt_2^26_parity_ok"] = bool(parity)
+  line["ntt_2^26_strong_scaling_efficiency"] = out.get("strong_scaling_efficiency", 1.0)
   line["ntt_2^26"] = out
   torch.cuda.empty_cache()
 
