@@ -84,9 +84,9 @@ def allgather_roots_from_nodes(nodes: torch.Tensor, group=None):
   all-gather of 32 bytes per rank and ONE device-to-host copy, without the round trip through the
   host that a root returned by stk_merkle_commit would take."""
   world, _ = _world(group)
-  out = torch.empty((world, 32), dtype=torch.uint8, device=nodes.device)
+  out = torch.empty(world * 32, dtype=torch.uint8, device=nodes.device)   # flat: the shape every backend accepts
   dist.all_gather_into_tensor(out, nodes[1].contiguous(), group=group)
-  host = out.cpu().numpy()
+  host = out.cpu().numpy().reshape(world, 32)
   return [host[r].tobytes() for r in range(world)]
 
 

@@ -137,6 +137,46 @@ def _ntt_worker(rank, world, port, logn, q):
       dist.destroy_process_group()
 
 
+def _comm_worker(rank, world, port, q):
+  """The sharded prover's exchanges (dist.NcclComm) over gloo on CPU tensors: subtree roots from
+  the ranks' node buffers, the one-owner-per-record byte sum, the column all-gather."""
+  try:
+    _init(rank, world, port)
+    from starks_b200 import dist as sd
+    comm = sd.NcclComm(torch.device("cpu"))
+    assert (comm.world, comm.rank) == (world, rank)
+    nodes = torch.zeros((16, 32), dtype=torch.uint8)
+    nodes[1] = torch.arange(32, dtype=torch.uint8) + rank
+    roots = sd.allgather_roots_from_nodes(nodes, None)
+    assert roots == [bytes((i + r) % 256 for i in range(32)) for r in range(world)]
+    top = sd.combine_subtree_roots(roots)
+    assert sorted(top) == list(range(1, 2 * world))
+    rec, k = 96, 10
+    buf = np.zeros(rec * k, dtype=np.uint8)
+    want = np.zeros(rec * k, dtype=np.uint8)
+    for i in range(k):
+      owner = (3 * i + 1) % world
+      val = np.arange(rec, dtype=np.uint8) * (i + 1) % 251 + 1
+      want[i * rec:(i + 1) * rec] = val
+      if owner == rank:
+        buf[i * rec:(i + 1) * rec] = val
+    got = comm.allreduce_bytes(buf)
+    assert (got == want).all()
+    lq = 8
+    col_local = (torch.arange(lq * 8, dtype=torch.int32).view(lq, 8) + 1000 * rank)
+    column = torch.empty((lq * world, 8), dtype=torch.int32)
+    comm.allgather_column(None, column, col_local)
+    for r in range(world):
+      assert torch.equal(column[r * lq:(r + 1) * lq], torch.arange(lq * 8, dtype=torch.int32).view(lq, 8) + 1000 * r)
+    q.put((rank, "ok"))
+  except Exception as e:  # pragma: no cover
+    import traceback
+    q.put((rank, "FAIL: " + traceback.format_exc()))
+  finally:
+    if dist.is_initialized():
+      dist.destroy_process_group()
+
+
 def _run(worker, world, *args):
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
@@ -159,6 +199,11 @@ def test_sharded_commit_plumbing(world):
 @pytest.mark.parametrize("world,logn", [(2, 6), (4, 7)])
 def test_four_step_layouts(world, logn):
   _run(_ntt_worker, world, logn)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_prover_exchanges(world):
+  _run(_comm_worker, world)
 
 
 def test_pack_rows_single_process():
