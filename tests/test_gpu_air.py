@@ -179,3 +179,28 @@ def test_prover_takes_a_device_witness_and_rejects_noncanonical_limbs(eng, oracl
   with pytest.raises(ValueError):
     S.mk_proof(bad, bnd)
   assert eng.count_noncanonical(eng.alloc(bad.nbytes).upload(bad).ptr, 2 * steps) == 1
+
+
+def test_device_traces_small_prime_field(eng, oracle):
+  """The run-time-modulus (Montgomery) instantiation of the device trace kernel: chunked affine
+  trace and a batch of non-linear traces over p = 31, against the host recurrence / the oracle."""
+  from starks_b200.air import witness_device, witness_limbs
+  from starks_b200.modp import IntegersModP
+  F = IntegersModP(31)
+  try:
+    sp = [{(0, 1): 1}, {(1, 0): 3, (0, 1): 1, (0, 0): 7}]
+    steps = 5000
+    d_w = witness_device(F, [4, 9], steps, 2, sp, engine=eng)
+    got = d_w.download((2, steps, 8))
+    d_w.free()
+    assert (got == witness_limbs(F, [4, 9], steps, 2, sp, engine=eng)).all()
+    ref = oracle.computational_trace(31, [4, 9], 64, sp)
+    assert oracle.from_limbs(got[0, :64]) == ref[0] and oracle.from_limbs(got[1, :64]) == ref[1]
+    sq = [{(2,): 1, (0,): 3}]
+    d_w = witness_device(F, [[i] for i in range(20)], 40, 1, sq, engine=eng, ntraces=20)
+    got = d_w.download((20, 1, 40, 8))
+    d_w.free()
+    for t in (0, 7, 19):
+      assert oracle.from_limbs(got[t, 0]) == oracle.computational_trace(31, [t], 40, sq)[0]
+  finally:
+    eng.set_field(P)
