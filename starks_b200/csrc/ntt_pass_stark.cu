@@ -28,6 +28,11 @@ static int launch_pass_r(stk_ctx* c, cudaStream_t s, const NttPass& P, const F& 
   return STK_OK;
 }
 
+// resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * STK_MINB)); the
+// A/B builds of tools/gpu_minb_ab.sh override it
+#ifndef STK_MINB
+#define STK_MINB 4
+#endif
 int stk_launch_pass_stark(stk_ctx* c, cudaStream_t s, const NttPass& P) {
-  return launch_pass_r<StarkField, 3, 128, 4, false>(c, s, P, StarkField());
+  return launch_pass_r<StarkField, 3, 128, STK_MINB, false>(c, s, P, StarkField());
 }
