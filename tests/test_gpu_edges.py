@@ -155,3 +155,27 @@ def test_direct_dft_cross_checks_the_fast_path(eng, oracle):
   eng.dft_generic(d_in.ptr, 6, 6, d_o.ptr, 6, 6, 1, pow(3, 5, 31))
   assert oracle.from_limbs(d_o.download((6, 8))) == oracle.fft_1d(31, [7, 0, 30, 4, 11, 2], pow(3, 5, 31))
   eng.set_field(P)
+
+
+def test_more_columns_than_a_grid_dimension(eng):
+  """A multi-pass transform puts the column index in gridDim.y (<= 65535): wider batches run as
+  consecutive column groups.  66 000 columns of 2^12: sampled columns equal their own
+  single-column transform, forward and inverse."""
+  import torch
+  n, batch = 1 << 12, 66000
+  w = pow(7, (P - 1) // n, P)
+  gen = torch.Generator(device="cuda")
+  gen.manual_seed(5)
+  x = torch.randint(0, 2**31 - 1, (batch, n, 8), dtype=torch.int32, device="cuda", generator=gen)
+  y = torch.empty_like(x)
+  torch.cuda.synchronize()
+  for inverse in (False, True):
+    eng.ntt(x.data_ptr(), n, n, y.data_ptr(), n, n, batch, w, inverse=inverse)
+    eng.sync()
+    one = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    for c in (0, 1, 32767, 32768, 65535, 65536, batch - 1):
+      eng.ntt(x[c].data_ptr(), n, n, one.data_ptr(), n, n, 1, w, inverse=inverse)
+      eng.sync()
+      assert torch.equal(one, y[c]), (inverse, c)
+  del x, y
+  torch.cuda.empty_cache()
